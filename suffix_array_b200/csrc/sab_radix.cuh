@@ -1,0 +1,252 @@
+// sab_radix.cuh -- hand-written LSD radix sort (8-bit digits) for (key, u32 payload) records.
+//
+//   radix_hist_kernel   one sweep over the keys -> 256-bin histograms of every digit place
+//   radix_scan_kernel   exclusive scans of those histograms + "this pass is a no-op" flags
+//   onesweep_kernel     one stable partition pass: keys staged through shared memory, ranked with
+//                       warp-level match_any, tile prefixes chained by decoupled look-back
+//                       (one look-back lane per bin), coalesced write-out from shared memory.
+//
+// Algorithmic traffic: histogram K*m bytes; each pass 2*(K+V)*m bytes.
+// Nothing here is a dense contraction; the bound is HBM bandwidth, tensor cores are not used.
+#pragma once
+#include "sab_common.cuh"
+
+#define SAB_RADIX_BITS 8
+#define SAB_RADIX_BINS 256
+#define SAB_MAX_PASSES 8
+
+// look-back word: [63:36] epoch (28 bits) | [35:34] flag | [33:0] count
+#define SAB_LB_VALUE_MASK ((1ull << 34) - 1ull)
+#define SAB_LB_FLAG_PARTIAL (1ull << 34)
+#define SAB_LB_FLAG_INCLUSIVE (2ull << 34)
+#define SAB_LB_FLAG_MASK (3ull << 34)
+#define SAB_LB_EPOCH_SHIFT 36
+#define SAB_LB_EPOCH_MAX ((1u << 28) - 1u)
+
+template <typename KeyT>
+struct KeyTraits;
+template <>
+struct KeyTraits<u32> {
+    static __device__ __forceinline__ u32 digit(u32 k, int shift) { return (k >> shift) & 0xffu; }
+    static __device__ __forceinline__ u32 max_key() { return 0xffffffffu; }
+};
+template <>
+struct KeyTraits<u64> {
+    static __device__ __forceinline__ u32 digit(u64 k, int shift) { return (u32)(k >> shift) & 0xffu; }
+    static __device__ __forceinline__ u64 max_key() { return ~0ull; }
+};
+
+// ------------------------------------------------------------------ histogram of all digit places
+#define SAB_HIST_THREADS 512
+#define SAB_HIST_ITEMS 8
+
+template <typename KeyT>
+__global__ void __launch_bounds__(SAB_HIST_THREADS)
+radix_hist_kernel(const KeyT* __restrict__ keys, u64 n, int begin_bit, int npass, u64* __restrict__ ghist) {
+    SAB_SHARED_ARRAY(u32, s_hist, SAB_MAX_PASSES * SAB_RADIX_BINS);
+    for (int i = threadIdx.x; i < SAB_MAX_PASSES * SAB_RADIX_BINS; i += SAB_HIST_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const u64 tile = (u64)SAB_HIST_THREADS * SAB_HIST_ITEMS;
+    const u64 ntiles = (n + tile - 1) / tile;
+    for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const u64 base = t * tile;
+        KeyT k[SAB_HIST_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SAB_HIST_ITEMS; ++j) {
+            const u64 idx = base + (u64)j * SAB_HIST_THREADS + threadIdx.x;
+            k[j] = idx < n ? keys[idx] : (KeyT)0;
+        }
+#pragma unroll
+        for (int j = 0; j < SAB_HIST_ITEMS; ++j) {
+            const u64 idx = base + (u64)j * SAB_HIST_THREADS + threadIdx.x;
+            if (idx < n) {
+                for (int p = 0; p < npass; ++p)
+                    atomicAdd(&s_hist[p * SAB_RADIX_BINS + KeyTraits<KeyT>::digit(k[j], begin_bit + p * SAB_RADIX_BITS)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * SAB_RADIX_BINS; i += SAB_HIST_THREADS) {
+        const u32 c = s_hist[i];
+        if (c) atomicAdd((unsigned long long*)&ghist[i], (unsigned long long)c);
+    }
+}
+
+// one block of 256 threads: gbase[p][d] = exclusive prefix of ghist[p][*]; skip[p] = 1 when every key
+// has the same digit at place p (the pass would be the identity permutation).
+__global__ void __launch_bounds__(SAB_RADIX_BINS)
+radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restrict__ gbase, u32* __restrict__ skip) {
+    SAB_SHARED_ARRAY(u64, s_wsum, 8);
+    SAB_SHARED_VAR(u32, s_full);
+    const u32 d = threadIdx.x, lane = lane_id(), w = warp_id();
+    for (int p = 0; p < npass; ++p) {
+        if (d == 0) s_full = 0;
+        __syncthreads();
+        const u64 c = ghist[p * SAB_RADIX_BINS + d];
+        if (c == n) s_full = 1;
+        u64 incl = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const u64 o = __shfl_up_sync(SAB_FULL, incl, s);
+            if ((int)lane >= s) incl += o;
+        }
+        if (lane == 31) s_wsum[w] = incl;
+        __syncthreads();
+        u64 woff = 0;
+        for (u32 i = 0; i < w; ++i) woff += s_wsum[i];
+        gbase[p * SAB_RADIX_BINS + d] = woff + incl - c;
+        if (d == 0) skip[p] = s_full;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ one onesweep pass
+template <typename KeyT, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
+struct OnesweepCfg {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr size_t KEY_BYTES = (size_t)TILE * sizeof(KeyT);
+    static constexpr size_t VAL_BYTES = HAS_VAL ? (size_t)TILE * sizeof(u32) : 0;
+    static constexpr size_t WHIST_BYTES = (size_t)WARPS * SAB_RADIX_BINS * sizeof(u32);
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * (sizeof(u32) + sizeof(u64));
+};
+
+// vals_in may be null when IOTA_VAL (payload = position of the record in the input).
+template <typename KeyT, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
+                u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ gbase,
+                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch) {
+    typedef OnesweepCfg<KeyT, HAS_VAL, IOTA_VAL, THREADS, ITEMS> Cfg;
+    static_assert(THREADS >= SAB_RADIX_BINS && THREADS % 32 == 0, "one look-back lane per bin");
+    constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE, WTILE = 32 * ITEMS;
+    SAB_DYN_SMEM(smem);
+    KeyT* s_keys = (KeyT*)smem;
+    u32* s_vals = (u32*)(smem + Cfg::KEY_BYTES);
+    u64* s_goff = (u64*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES);          // [256] global offset - local start
+    u32* s_whist = (u32*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES + SAB_RADIX_BINS * sizeof(u64));  // [WARPS][256]
+    u32* s_binstart = s_whist + WARPS * SAB_RADIX_BINS;                     // [256]
+    SAB_SHARED_VAR(u32, s_tile);
+    SAB_SHARED_ARRAY(u32, s_wsum, 8);
+
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+    for (int i = tid; i < WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 tile_base = (u64)tile * TILE;
+    const u64 remaining = n - tile_base;
+    const u32 valid = remaining < (u64)TILE ? (u32)remaining : (u32)TILE;
+
+    // ---- load (warp-striped: item k of lane l is record w*WTILE + k*32 + l of the tile)
+    KeyT keys[ITEMS];
+    u32 vals[ITEMS];
+    u32 ranks[ITEMS];
+    const u32 wofs = w * WTILE + lane;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 o = wofs + k * 32;
+        keys[k] = o < valid ? keys_in[tile_base + o] : KeyTraits<KeyT>::max_key();
+    }
+    if (HAS_VAL) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 o = wofs + k * 32;
+            if (IOTA_VAL) vals[k] = (u32)(tile_base + o);
+            else vals[k] = o < valid ? vals_in[tile_base + o] : 0u;
+        }
+    }
+
+    // ---- rank inside the warp (stable in (k, lane) order)
+    u32* wh = s_whist + w * SAB_RADIX_BINS;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 d = KeyTraits<KeyT>::digit(keys[k], shift);
+        const u32 peers = __match_any_sync(SAB_FULL, d);
+        const u32 leader = (u32)(__ffs((int)peers) - 1);
+        u32 old = 0;
+        if (lane == leader) {
+            old = wh[d];
+            wh[d] = old + (u32)__popc(peers);
+        }
+        old = __shfl_sync(SAB_FULL, old, (int)leader);
+        ranks[k] = old + (u32)__popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per bin: exclusive offsets of the warps, tile count; publish the partial
+    u32 my_count = 0;
+    u64* lb = lookback + (u64)tile * SAB_RADIX_BINS + tid;
+    const u64 etag = (u64)epoch << SAB_LB_EPOCH_SHIFT;
+    if (tid < SAB_RADIX_BINS) {
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ++ww) {
+            const u32 c = s_whist[ww * SAB_RADIX_BINS + tid];
+            s_whist[ww * SAB_RADIX_BINS + tid] = run;
+            run += c;
+        }
+        my_count = run;
+        st_relaxed_u64(lb, etag | (tile == 0 ? SAB_LB_FLAG_INCLUSIVE : SAB_LB_FLAG_PARTIAL) | (u64)my_count);
+    }
+    // ---- block-exclusive scan of the 256 bin counts -> local start of every bin in the tile
+    {
+        u32 incl = warp_incl_sum(my_count);
+        if (tid < SAB_RADIX_BINS && lane == 31) s_wsum[w] = incl;
+        __syncthreads();
+        if (tid < SAB_RADIX_BINS) {
+            u32 woff = 0;
+            for (u32 i = 0; i < w; ++i) woff += s_wsum[i];
+            s_binstart[tid] = woff + incl - my_count;
+        }
+    }
+    // ---- decoupled look-back, one lane per bin
+    if (tid < SAB_RADIX_BINS) {
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                const u64 v = ld_relaxed_u64(lookback + (u64)t * SAB_RADIX_BINS + tid);
+                const u64 f = v & SAB_LB_FLAG_MASK;
+                if ((v >> SAB_LB_EPOCH_SHIFT) != (u64)epoch || f == 0) {
+                    SAB_SPIN_PAUSE();
+                    continue;
+                }
+                excl += v & SAB_LB_VALUE_MASK;
+                if (f == SAB_LB_FLAG_INCLUSIVE) break;
+                --t;
+            }
+            st_relaxed_u64(lb, etag | SAB_LB_FLAG_INCLUSIVE | (excl + (u64)my_count));
+        }
+        s_goff[tid] = gbase[tid] + excl - (u64)s_binstart[tid];
+    }
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 d = KeyTraits<KeyT>::digit(keys[k], shift);
+        const u32 pos = s_binstart[d] + s_whist[w * SAB_RADIX_BINS + d] + ranks[k];
+        s_keys[pos] = keys[k];
+        if (HAS_VAL) s_vals[pos] = vals[k];
+    }
+    __syncthreads();
+
+    // ---- coalesced write-out: consecutive shared slots of one bin are consecutive in global memory
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 p = tid + k * THREADS;
+        if (p < valid) {
+            const KeyT key = s_keys[p];
+            const u64 dst = s_goff[KeyTraits<KeyT>::digit(key, shift)] + p;
+            keys_out[dst] = key;
+            if (HAS_VAL) vals_out[dst] = s_vals[p];
+        }
+    }
+}
+
+__global__ void iota_kernel(u32* __restrict__ out, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u32)i;
+}

@@ -1,0 +1,473 @@
+// sab_saca.cuh -- suffix-array construction by GPU prefix doubling.  Replaces the body of
+// saca() (/root/reference/src/saca.rs:9-15), i.e. `sa[0] = n; divsufsort(s, sa[1..])`.
+//
+//   1. alphabet_hist        256-bin byte histogram -> sigma, code LUT (codes 1..sigma; 0 = past the end)
+//   2. pack_keys            key[i] = first k codes of suffix i, MSB first, b = ceil(log2(sigma+1)) bits
+//                           each, k = floor(64/b).  Code 0 past the end makes a proper prefix sort first
+//                           and keeps real 0x00 bytes distinct from padding.
+//   3. radix sort (key, i)  sab_sort.cuh
+//   4. init_ranks           head flags -> rank[i] = SA position of the first suffix of i's group;
+//                           sa[pos] = i; groups of size > 1 are compacted into the active list
+//   5. rounds, h = k, 2k, 4k, ...   gather r2 = rank[i+h]; sort active by (r1, r2); re-rank with a
+//                           chained scan; settled (singleton) suffixes are written to sa[] and dropped.
+//
+// Invariants: after a round at depth h two suffixes share a rank iff their first h
+// symbols agree; rank = SA position of the group head, so a singleton's rank is its final position;
+// rank[n] = 0 (empty suffix); every active i has i + h <= n.
+#pragma once
+#include "sab_context.cuh"
+#include "sab_sort.cuh"
+
+#define SAB_SCAN_THREADS 256
+#define SAB_SCAN_ITEMS 8
+#define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
+
+// ------------------------------------------------------------------ 1. alphabet
+__global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ hist) {
+    SAB_SHARED_ARRAY(u32, s_h, 256);
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 head = (16 - ((u64)(uintptr_t)text & 15)) & 15;  // bytes before the first 16-byte boundary
+    if (head > n) head = n;
+    for (u64 i = gtid; i < head; i += stride) atomicAdd(&s_h[text[i]], 1u);
+    const u64 nvec = (n - head) / 16;
+    const uint4* tv = (const uint4*)(text + head);
+    for (u64 i = gtid; i < nvec; i += stride) {
+        const uint4 v = tv[i];
+        const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&s_h[w[j] & 0xff], 1u);
+            atomicAdd(&s_h[(w[j] >> 8) & 0xff], 1u);
+            atomicAdd(&s_h[(w[j] >> 16) & 0xff], 1u);
+            atomicAdd(&s_h[w[j] >> 24], 1u);
+        }
+    }
+    for (u64 i = head + nvec * 16 + gtid; i < n; i += stride) atomicAdd(&s_h[text[i]], 1u);
+    __syncthreads();
+    const u32 c = s_h[threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], c);
+}
+
+// ------------------------------------------------------------------ 2. packed initial keys
+#define SAB_PACK_THREADS 256
+#define SAB_PACK_ITEMS 8
+#define SAB_PACK_TILE (SAB_PACK_THREADS * SAB_PACK_ITEMS)
+
+// lut[c] = code of byte c (1..sigma).  key bits [0, k*b) are used.
+__global__ void __launch_bounds__(SAB_PACK_THREADS)
+pack_keys_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, int b, int k, u64* __restrict__ keys) {
+    SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
+    SAB_SHARED_ARRAY(u16, s_lut, 256);
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * SAB_PACK_TILE;
+    for (int o = threadIdx.x; o < SAB_PACK_TILE + 64; o += SAB_PACK_THREADS) {
+        const u64 i = base + o;
+        s_code[o] = i < n ? s_lut[text[i]] : (u16)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
+        const int o = threadIdx.x + j * SAB_PACK_THREADS;
+        const u64 i = base + o;
+        if (i < n) {
+            u64 key = 0;
+            for (int t = 0; t < k; ++t) key = (key << b) | (u64)s_code[o + t];
+            keys[i] = key;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ block-wide exclusive scan of a POD
+template <typename T, typename Op>
+__device__ __forceinline__ T shfl_up_pod(T v, int d) {
+    constexpr int W = sizeof(T) / 4;
+    union {
+        T t;
+        u32 w[W];
+    } u;
+    u.t = v;
+#pragma unroll
+    for (int i = 0; i < W; ++i) u.w[i] = __shfl_up_sync(SAB_FULL, u.w[i], d);
+    return u.t;
+}
+
+// returns the exclusive prefix of `v` over the threads of the block; `total` = block aggregate (all threads)
+template <typename T, typename Op, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& total) {
+    constexpr int WARPS = THREADS / 32;
+    SAB_SHARED_ARRAY(T, s_wagg, WARPS);
+    const u32 lane = lane_id(), w = warp_id();
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = shfl_up_pod<T, Op>(incl, d);
+        if ((int)lane >= d) incl = op(o, incl);
+    }
+    if (lane == 31) s_wagg[w] = incl;
+    __syncthreads();
+    T wprefix = identity;
+    T tot = identity;
+#pragma unroll
+    for (int i = 0; i < WARPS; ++i) {
+        const T a = s_wagg[i];
+        if (i < (int)w) wprefix = op(wprefix, a);
+        tot = op(tot, a);
+    }
+    T excl = shfl_up_pod<T, Op>(incl, 1);
+    if (lane == 0) excl = identity;
+    total = tot;
+    __syncthreads();  // s_wagg reusable
+    return op(wprefix, excl);
+}
+
+// ------------------------------------------------------------------ 4. ranks after the initial sort
+struct RankScan {
+    u32 head;  // largest index of a group head seen so far (index 0 is always a head)
+    u32 cnt;   // number of active (non-singleton) records seen so far
+};
+struct RankScanOp {
+    __device__ __forceinline__ RankScan operator()(const RankScan& a, const RankScan& b) const {
+        RankScan r;
+        r.head = a.head > b.head ? a.head : b.head;
+        r.cnt = a.cnt + b.cnt;
+        return r;
+    }
+};
+
+// K, I: records sorted by key.  Writes rank[I[j]] = 1 + (index of the head of j's group),
+// sa[j+1] = I[j], sa[0] = n, and compacts records of groups larger than one into (act_r1, act_idx).
+__global__ void __launch_bounds__(SAB_SCAN_THREADS)
+init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32* __restrict__ rank,
+                  u32* __restrict__ sa, u32* __restrict__ act_r1, u32* __restrict__ act_idx, u32* __restrict__ d_count,
+                  TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
+    SAB_SHARED_VAR(u32, s_tile);
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 j0 = (u64)tile * SAB_SCAN_TILE + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+    u64 key[SAB_SCAN_ITEMS + 2];  // key[0] = predecessor, key[ITEMS+1] = successor
+    u32 idx[SAB_SCAN_ITEMS];
+    const u64 SENT = ~0ull;  // never compared: guarded by index tests below
+    key[0] = (j0 > 0 && j0 - 1 < n) ? K[j0 - 1] : SENT;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        key[k + 1] = j < n ? K[j] : SENT;
+        idx[k] = j < n ? I[j] : 0u;
+    }
+    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < n) ? K[j0 + SAB_SCAN_ITEMS] : SENT;
+
+    RankScan mine;
+    mine.head = 0;
+    mine.cnt = 0;
+    u32 headbits = 0, activebits = 0;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        if (j < n) {
+            const bool head = (j == 0) || key[k + 1] != key[k];
+            const bool next_head = (j + 1 >= n) || key[k + 2] != key[k + 1];
+            if (head) {
+                headbits |= 1u << k;
+                mine.head = (u32)j;
+            }
+            if (!(head && next_head)) {
+                activebits |= 1u << k;
+                mine.cnt++;
+            }
+        }
+    }
+    RankScan ident;
+    ident.head = 0;
+    ident.cnt = 0;
+    RankScan total;
+    RankScan excl = block_exclusive_scan<RankScan, RankScanOp, SAB_SCAN_THREADS>(mine, RankScanOp(), ident, total);
+    RankScan prefix = tile_exclusive_prefix<RankScan, RankScanOp>(st, tile, total, RankScanOp(), ident);
+    RankScan run = RankScanOp()(prefix, excl);
+    if (tile == 0 && threadIdx.x == 0) sa[0] = (u32)n;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        if (j < n) {
+            if (headbits & (1u << k)) run.head = (u32)j;
+            const u32 r = run.head + 1u;
+            rank[idx[k]] = r;
+            sa[j + 1] = idx[k];
+            if (activebits & (1u << k)) {
+                act_r1[run.cnt] = r;
+                act_idx[run.cnt] = idx[k];
+                run.cnt++;
+            }
+        }
+    }
+    const u64 last = n - 1;
+    if (last >= j0 && last < j0 + SAB_SCAN_ITEMS) *d_count = run.cnt;
+    if (tile == 0 && threadIdx.x == 0) rank[n] = 0u;
+}
+
+// ------------------------------------------------------------------ 5a. gather the second rank
+#define SAB_GATHER_THREADS 256
+#define SAB_GATHER_ITEMS 4
+
+// key64[j] = (r1[j] << 32) | rank[idx[j] + h]
+__global__ void __launch_bounds__(SAB_GATHER_THREADS)
+gather_rank2_kernel(const u32* __restrict__ act_r1, const u32* __restrict__ act_idx, u64 m, u64 h,
+                    const u32* __restrict__ rank, u64* __restrict__ key64) {
+    const u64 j0 = ((u64)blockIdx.x * SAB_GATHER_THREADS + threadIdx.x) * SAB_GATHER_ITEMS;
+    if (j0 + SAB_GATHER_ITEMS <= m) {
+        const uint4 r1 = *(const uint4*)(act_r1 + j0);
+        const uint4 ix = *(const uint4*)(act_idx + j0);
+        const u32 a = rank[(u64)ix.x + h], b = rank[(u64)ix.y + h], c = rank[(u64)ix.z + h], d = rank[(u64)ix.w + h];
+        ulonglong2 o0, o1;
+        o0.x = ((u64)r1.x << 32) | a;
+        o0.y = ((u64)r1.y << 32) | b;
+        o1.x = ((u64)r1.z << 32) | c;
+        o1.y = ((u64)r1.w << 32) | d;
+        *(ulonglong2*)(key64 + j0) = o0;
+        *(ulonglong2*)(key64 + j0 + 2) = o1;
+    } else {
+        for (u64 j = j0; j < m; ++j) key64[j] = ((u64)act_r1[j] << 32) | rank[(u64)act_idx[j] + h];
+    }
+}
+
+// ------------------------------------------------------------------ 5b. re-rank + compaction
+struct RerankScan {
+    u32 ogs;  // index (in the active array) of the head of the old group
+    u32 nhs;  // index of the head of the new (refined) group
+    u32 cnt;  // records kept (still unsettled) so far
+};
+struct RerankScanOp {
+    __device__ __forceinline__ RerankScan operator()(const RerankScan& a, const RerankScan& b) const {
+        RerankScan r;
+        r.ogs = a.ogs > b.ogs ? a.ogs : b.ogs;
+        r.nhs = a.nhs > b.nhs ? a.nhs : b.nhs;
+        r.cnt = a.cnt + b.cnt;
+        return r;
+    }
+};
+
+// S, I: active records sorted by (r1, r2) (S = r1<<32 | r2).  For record j:
+//   new_r1 = r1 + (head index of its new group - head index of its old group)
+//   changed rank  -> rank[I[j]] = new_r1
+//   singleton     -> sa[new_r1] = I[j] (final), dropped
+//   otherwise     -> appended to (out_r1, out_idx)
+__global__ void __launch_bounds__(SAB_SCAN_THREADS)
+rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
+              u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ d_count, TileState<RerankScan> st,
+              u32* __restrict__ ticket, u32 ticket_base) {
+    SAB_SHARED_VAR(u32, s_tile);
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 j0 = (u64)tile * SAB_SCAN_TILE + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+    u64 key[SAB_SCAN_ITEMS + 2];
+    u32 idx[SAB_SCAN_ITEMS];
+    key[0] = (j0 > 0 && j0 - 1 < m) ? S[j0 - 1] : 0ull;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        key[k + 1] = j < m ? S[j] : 0ull;
+        idx[k] = j < m ? I[j] : 0u;
+    }
+    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < m) ? S[j0 + SAB_SCAN_ITEMS] : 0ull;
+
+    RerankScan mine;
+    mine.ogs = 0;
+    mine.nhs = 0;
+    mine.cnt = 0;
+    u32 oldbits = 0, newbits = 0, keepbits = 0;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        if (j < m) {
+            const bool oldhead = (j == 0) || (u32)(key[k + 1] >> 32) != (u32)(key[k] >> 32);
+            const bool newhead = (j == 0) || key[k + 1] != key[k];
+            const bool next_newhead = (j + 1 >= m) || key[k + 2] != key[k + 1];
+            if (oldhead) {
+                oldbits |= 1u << k;
+                mine.ogs = (u32)j;
+            }
+            if (newhead) {
+                newbits |= 1u << k;
+                mine.nhs = (u32)j;
+            }
+            if (!(newhead && next_newhead)) {
+                keepbits |= 1u << k;
+                mine.cnt++;
+            }
+        }
+    }
+    RerankScan ident;
+    ident.ogs = 0;
+    ident.nhs = 0;
+    ident.cnt = 0;
+    RerankScan total;
+    RerankScan excl = block_exclusive_scan<RerankScan, RerankScanOp, SAB_SCAN_THREADS>(mine, RerankScanOp(), ident, total);
+    RerankScan prefix = tile_exclusive_prefix<RerankScan, RerankScanOp>(st, tile, total, RerankScanOp(), ident);
+    RerankScan run = RerankScanOp()(prefix, excl);
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = j0 + k;
+        if (j < m) {
+            if (oldbits & (1u << k)) run.ogs = (u32)j;
+            if (newbits & (1u << k)) run.nhs = (u32)j;
+            const u32 r1 = (u32)(key[k + 1] >> 32);
+            const u32 nr = r1 + (run.nhs - run.ogs);
+            if (nr != r1) rank[idx[k]] = nr;
+            if (keepbits & (1u << k)) {
+                out_r1[run.cnt] = nr;
+                out_idx[run.cnt] = idx[k];
+                run.cnt++;
+            } else {
+                sa[nr] = idx[k];
+            }
+        }
+    }
+    const u64 last = m - 1;
+    if (last >= j0 && last < j0 + SAB_SCAN_ITEMS) *d_count = run.cnt;
+}
+
+// ------------------------------------------------------------------ driver (device pointers)
+static inline int sab_ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
+    int b = 0;
+    while (b < 64 && (1ull << b) < x) ++b;
+    return b;
+}
+
+// bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
+static inline size_t sab_saca_workspace_bytes(u64 n) {
+    const size_t N = (size_t)n + 8;
+    return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) + 4096;
+}
+
+// d_text: n bytes; d_sa: n+1 u32; both device memory.  Work is enqueued on c->stream and the
+// stream is synchronised before returning.
+static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
+    SabStats& S = c->stats;
+    memset(&S, 0, sizeof(S));
+    S.n = n;
+    cudaStream_t st = c->stream;
+    if (n == 0) {
+        SAB_CUDA_TRY(cudaMemsetAsync(d_sa, 0, sizeof(u32), st));
+        SAB_CUDA_TRY(cudaStreamSynchronize(st));
+        return SAB_OK;
+    }
+    SAB_TRY(sab_arena_reserve(c, sab_saca_workspace_bytes(n)));
+    c->arena_used = 0;
+    SortBuffers<u64> buf;
+    buf.k[0] = sab_arena_take<u64>(c, n + 8);
+    buf.k[1] = sab_arena_take<u64>(c, n + 8);
+    buf.v[0] = sab_arena_take<u32>(c, n + 8);
+    buf.v[1] = sab_arena_take<u32>(c, n + 8);
+    u32* r1buf = sab_arena_take<u32>(c, n + 8);
+    u32* rank = sab_arena_take<u32>(c, n + 9);
+    buf.cur = 0;
+    SAB_TRY(sab_ensure_scan(c, (size_t)div_up64(n, SAB_SCAN_TILE)));
+
+    // 1. alphabet
+    sab_prof_begin(c, 2);
+    u32* d_hist = c->d_counters + 16;  // 256 words inside the counters block
+    SAB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(u32), st));
+    {
+        u64 blocks = div_up64(n, 256 * 64);
+        const u64 bmax = (u64)c->sm_count * 8;
+        if (blocks > bmax) blocks = bmax;
+        SAB_LAUNCH(alphabet_hist_kernel, (unsigned)blocks, 256, 0, st, d_text, n, d_hist);
+        SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
+    }
+    u32 h_hist[256];
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 64, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(h_hist, c->h_small + 64, sizeof(h_hist));
+    u16 lut[256];
+    u32 sigma = 0;
+    for (int ch = 0; ch < 256; ++ch) {
+        if (h_hist[ch]) ++sigma;
+        lut[ch] = (u16)(h_hist[ch] ? sigma : 0);
+    }
+    int b = sab_ceil_log2_u64((u64)sigma + 1);  // codes 0..sigma
+    if (b < 1) b = 1;
+    const int k = 64 / b;
+    S.sigma = sigma;
+    S.bits_per_symbol = (u32)b;
+    S.symbols_per_key = (u32)k;
+    u16* d_lut = (u16*)(c->d_counters + 16 + 256);
+    memcpy(c->h_small + 384, lut, sizeof(lut));  // pinned staging: the async copy must not read the stack later
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
+
+    // 2. packed keys
+    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, (const u16*)d_lut,
+               b, k, buf.k[0]);
+    sab_prof_end(c);
+    SAB_LAUNCH_CHECK();
+    S.kernel_launches++;
+
+    // 3. sort (key, i)
+    SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, k * b, /*iota=*/true, &S.passes[0]));
+
+    // 4. ranks, SA skeleton, active list
+    u32* d_m = c->d_counters;
+    u32* act_idx = buf.v[buf.cur ^ 1];
+    {
+        const u64 tiles = div_up64(n, SAB_SCAN_TILE);
+        TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
+        sab_prof_begin(c, 3);
+        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)buf.k[buf.cur],
+                   (const u32*)buf.v[buf.cur], n, rank, d_sa, r1buf, act_idx, d_m, ts, c->d_ticket, c->ticket_host);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        c->ticket_host += (u32)tiles;
+        S.kernel_launches++;
+    }
+    buf.cur ^= 1;  // v[cur] now holds act_idx; k[cur] is free for the composite keys
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    u64 m = c->h_small[0];
+    S.active[0] = m;
+
+    // 5. doubling rounds
+    u64 h = (u64)k;
+    u32 round = 0;
+    const int rank_bits = sab_ceil_log2_u64(n + 2);
+    while (m > 0) {
+        ++round;
+        if (round >= SAB_MAX_ROUNDS || h > n) {
+            sab_set_error("prefix doubling did not converge (round %u, h=%llu, m=%llu)", round, (unsigned long long)h,
+                          (unsigned long long)m);
+            return SAB_ERR_INTERNAL;
+        }
+        sab_prof_begin(c, 4);
+        SAB_LAUNCH(gather_rank2_kernel, (unsigned)div_up64(m, (u64)SAB_GATHER_THREADS * SAB_GATHER_ITEMS), SAB_GATHER_THREADS,
+                   0, st, (const u32*)r1buf, (const u32*)buf.v[buf.cur], m, h, (const u32*)rank, buf.k[buf.cur]);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
+        SAB_TRY(sab_radix_sort<u64>(c, buf, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+        {
+            const u64 tiles = div_up64(m, SAB_SCAN_TILE);
+            TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
+            sab_prof_begin(c, 3);
+            SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)buf.k[buf.cur],
+                       (const u32*)buf.v[buf.cur], m, rank, d_sa, r1buf, buf.v[buf.cur ^ 1], d_m, ts, c->d_ticket,
+                       c->ticket_host);
+            sab_prof_end(c);
+            SAB_LAUNCH_CHECK();
+            c->ticket_host += (u32)tiles;
+            S.kernel_launches++;
+        }
+        buf.cur ^= 1;
+        SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SAB_CUDA_TRY(cudaStreamSynchronize(st));
+        m = c->h_small[0];
+        S.active[round] = m;
+        h *= 2;
+    }
+    S.rounds = round;
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SAB_OK;
+}
