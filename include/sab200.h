@@ -72,6 +72,46 @@ int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus);
  * bytes, d_sa receives n+1 entries.  Used to time the device pipeline without PCIe. */
 int32_t sab200_saca_device(const uint8_t* d_s, uint64_t n, uint32_t* d_sa, int32_t device);
 
+/* ---- bucket index -------------------------------------------------------------------------
+ * Replaces the body of SuffixArray::enable_buckets (src/sa.rs:89-119): writes the SAB200_BKT_LEN
+ * inclusive right-boundaries of the 2-byte-prefix buckets, layout
+ * [$; (0,$),(0,0)..(0,255); ...; (255,$)..(255,255)] (src/sa.rs:94), slot(c0,$) = c0*257+1,
+ * slot(c0,c1) = c0*257+c1+2 (src/sa.rs:103,107), u32 wrap-around sums (src/sa.rs:112-116).
+ * Reads the text only, like the reference.  `s`, `bkt` are host buffers. */
+int32_t sab200_enable_buckets(const uint8_t* s, uint64_t n, uint32_t* bkt);
+
+/* ---- integrity -----------------------------------------------------------------------------
+ * Replaces SuffixArray::check_integrity behind from_parts (src/sa.rs:57-84) with a linear-time
+ * equivalent (permutation via the inverse array, then neighbour order through the first byte and
+ * the ranks of the tails).  Returns 1 (valid), 0 (not the suffix array of s; also when
+ * sa_len != n+1, src/sa.rs:73-75, or an entry exceeds n, where the reference would panic), <0 error. */
+int32_t sab200_check(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len);
+
+/* ---- batched queries -----------------------------------------------------------------------
+ * A resident copy of (text, SA, optional bucket table) on `ngpus` GPUs (replicated; queries are
+ * sharded across the replicas, no collective).  bkt_or_null = NULL means "buckets not enabled"
+ * (get_bucket then returns the whole array, src/sa.rs:141-143).  Host buffers; copied, not kept. */
+typedef struct sab200_index sab200_index;
+sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, const uint32_t* bkt_or_null,
+                                  int32_t ngpus);
+void sab200_index_destroy(sab200_index* ix);
+
+/* Patterns are concatenated in `pats`; pattern q is pats[offs[q] .. offs[q+1]) (np+1 offsets).
+ *
+ * search_all (src/sa.rs:173-204): lo[q], hi[q] are GLOBAL suffix-array indices such that the slice
+ * the reference returns is &sa[lo[q]..hi[q]] (SA order).  An empty pattern yields [0, n+1).
+ * contains  (src/sa.rs:164-170): out[q] = 1/0.
+ * search_lcp (src/sa.rs:207-253): [start[q], end[q]) is the text range the reference returns. */
+int32_t sab200_search_all_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np,
+                                uint32_t* lo, uint32_t* hi);
+int32_t sab200_contains_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np, uint8_t* out);
+int32_t sab200_search_lcp_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np,
+                                uint32_t* start, uint32_t* end);
+/* search_all with DEVICE pattern / result buffers on the GPU of replica 0 (kernel-only timing);
+ * d_pats must be followed by at least 8 readable bytes. */
+int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t np,
+                                       uint32_t* d_lo, uint32_t* d_hi);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 int32_t sab200_get_stats(sab200_stats* out);
 void sab200_set_profiling(int32_t on); /* per-launch CUDA events for the stats above */

@@ -4,6 +4,7 @@
 #include "sab_common.cuh"
 #include "sab_context.cuh"
 #include "sab_saca.cuh"
+#include "sab_search.cuh"
 
 #include <chrono>
 #include <cstdlib>
@@ -276,6 +277,304 @@ int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
     g_last_stats = c->stats;
     return rc;
 }
+
+}  // extern "C"
+
+// ---- buckets -------------------------------------------------------------------------------
+static int buckets_device(SabContext* c, const u8* d_text, u64 n, u32* d_bkt) {
+    cudaStream_t st = c->stream;
+    SAB_CUDA_TRY(cudaMemsetAsync(d_bkt, 0, SAB_BKT_LEN * sizeof(u32), st));
+    if (n > 0) {
+        u32* d_hist = c->d_counters + 16;
+        SAB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(u32), st));
+        u64 blocks = div_up64(n, 256 * 64);
+        const u64 bmax = (u64)c->sm_count * 8;
+        if (blocks > bmax) blocks = bmax;
+        SAB_LAUNCH(alphabet_hist_kernel, (unsigned)blocks, 256, 0, st, d_text, n, d_hist);
+        SAB_LAUNCH_CHECK();
+        SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 64, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SAB_CUDA_TRY(cudaStreamSynchronize(st));
+        u16 lut[256];
+        u32 sigma = 0;
+        for (int ch = 0; ch < 256; ++ch) {
+            if (c->h_small[64 + ch]) ++sigma;
+            lut[ch] = (u16)(c->h_small[64 + ch] ? sigma : 0);
+        }
+        u16* d_lut = (u16*)(c->d_counters + 16 + 256);
+        memcpy(c->h_small + 384, lut, sizeof(lut));
+        SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
+        const size_t tab_bytes = (size_t)sigma * (sigma + 1) * sizeof(u32);
+        const int dense = tab_bytes <= 160 * 1024;
+        const size_t smem = dense ? tab_bytes : 0;
+#ifndef SAB_EMU
+        SAB_CUDA_TRY(cudaFuncSetAttribute(bucket_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+#endif
+        u64 pblocks = div_up64(n, 256 * 64);
+        const u64 pmax = (u64)c->sm_count * (smem > 64 * 1024 ? 1 : 4);
+        if (pblocks > pmax) pblocks = pmax;
+        SAB_LAUNCH(bucket_pairs_kernel, (unsigned)pblocks, 256, smem, st, d_text, n, (const u16*)d_lut, sigma, dense, d_bkt);
+        SAB_LAUNCH_CHECK();
+    }
+    SAB_LAUNCH(bucket_scan_kernel, 1, 1024, 0, st, d_bkt);
+    SAB_LAUNCH_CHECK();
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_enable_buckets(const uint8_t* s, uint64_t n, uint32_t* bkt) {
+    if (!bkt || (n > 0 && !s) || n > SAB200_MAX_LENGTH) {
+        sab_set_error("sab200_enable_buckets: bad arguments");
+        return SAB_ERR_ARGS;
+    }
+    SabContext* c = sab_get_context(0);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t text_bytes = sab_align_up((size_t)n + 64, 256);
+    SAB_TRY(sab_arena_reserve(c, text_bytes + SAB_BKT_LEN * sizeof(u32) + 1024));
+    u8* d_s = (u8*)c->arena;
+    u32* d_bkt = (u32*)(c->arena + text_bytes);
+    if (n) SAB_CUDA_TRY(cudaMemcpyAsync(d_s, s, n, cudaMemcpyHostToDevice, c->stream));
+    SAB_TRY(buckets_device(c, d_s, n, d_bkt));
+    SAB_CUDA_TRY(cudaMemcpyAsync(bkt, d_bkt, SAB_BKT_LEN * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
+// ---- integrity check -----------------------------------------------------------------------
+extern "C" int32_t sab200_check(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len) {
+    if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH) {
+        sab_set_error("sab200_check: bad arguments");
+        return SAB_ERR_ARGS;
+    }
+    if (sa_len != n + 1) return 0;  // src/sa.rs:73-75
+    SabContext* c = sab_get_context(0);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t text_bytes = sab_align_up((size_t)n + 64, 256);
+    const size_t arr_bytes = sab_align_up(((size_t)n + 2) * sizeof(u32), 256);
+    SAB_TRY(sab_arena_reserve(c, text_bytes + 2 * arr_bytes + 1024));
+    u8* d_s = (u8*)c->arena;
+    u32* d_sa = (u32*)(c->arena + text_bytes);
+    u32* d_isa = (u32*)(c->arena + text_bytes + arr_bytes);
+    u32* d_flag = c->d_counters + 8;
+    cudaStream_t st = c->stream;
+    SAB_CUDA_TRY(cudaMemsetAsync(d_s, 0, text_bytes, st));
+    if (n) SAB_CUDA_TRY(cudaMemcpyAsync(d_s, s, n, cudaMemcpyHostToDevice, st));
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_sa, sa, sa_len * sizeof(u32), cudaMemcpyHostToDevice, st));
+    SAB_CUDA_TRY(cudaMemsetAsync(d_isa, 0xff, arr_bytes, st));
+    SAB_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(u32), st));
+    const unsigned blocks = (unsigned)div_up64(sa_len, 256);
+    SAB_LAUNCH(sufcheck_scatter_kernel, blocks, 256, 0, st, (const u32*)d_sa, sa_len, n, d_isa, d_flag);
+    SAB_LAUNCH_CHECK();
+    SAB_LAUNCH(sufcheck_order_kernel, blocks, 256, 0, st, (const u8*)d_s, (const u32*)d_sa, sa_len, n, (const u32*)d_isa, d_flag);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_flag, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    return c->h_small[0] ? 0 : 1;
+}
+
+// ---- resident index + batched queries ------------------------------------------------------
+struct SabReplica {
+    SabContext* ctx = nullptr;
+    u8* d_text = nullptr;
+    u32* d_sa = nullptr;
+    u32* d_bkt = nullptr;
+    // query scratch (grow-only)
+    u8* d_pats = nullptr;
+    size_t pats_cap = 0;
+    u64* d_offs = nullptr;
+    u32* d_out0 = nullptr;
+    u32* d_out1 = nullptr;
+    size_t np_cap = 0;
+};
+struct sab200_index {
+    u64 n = 0;
+    bool has_bkt = false;
+    std::vector<SabReplica> rep;
+    std::mutex mu;
+};
+
+static void replica_free(SabReplica& r) {
+    if (!r.ctx) return;
+    cudaSetDevice(r.ctx->device);
+    cudaFree(r.d_text);
+    cudaFree(r.d_sa);
+    cudaFree(r.d_bkt);
+    cudaFree(r.d_pats);
+    cudaFree(r.d_offs);
+    cudaFree(r.d_out0);
+    cudaFree(r.d_out1);
+    r = SabReplica();
+}
+
+static int replica_init(SabReplica& r, int device, const u8* s, u64 n, const u32* sa, const u32* bkt) {
+    r.ctx = sab_get_context(device);
+    if (!r.ctx) return SAB_ERR_CUDA;
+    SAB_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = r.ctx->stream;
+    const size_t text_bytes = sab_align_up((size_t)n + 64, 256);
+    SAB_CUDA_TRY(cudaMalloc(&r.d_text, text_bytes));
+    SAB_CUDA_TRY(cudaMalloc(&r.d_sa, ((size_t)n + 1) * sizeof(u32)));
+    SAB_CUDA_TRY(cudaMemsetAsync(r.d_text, 0, text_bytes, st));
+    if (n) SAB_CUDA_TRY(cudaMemcpyAsync(r.d_text, s, n, cudaMemcpyHostToDevice, st));
+    SAB_CUDA_TRY(cudaMemcpyAsync(r.d_sa, sa, ((size_t)n + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (bkt) {
+        SAB_CUDA_TRY(cudaMalloc(&r.d_bkt, SAB_BKT_LEN * sizeof(u32)));
+        SAB_CUDA_TRY(cudaMemcpyAsync(r.d_bkt, bkt, SAB_BKT_LEN * sizeof(u32), cudaMemcpyHostToDevice, st));
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SAB_OK;
+}
+
+extern "C" sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, const uint32_t* bkt_or_null,
+                                  int32_t ngpus) {
+    if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH || ngpus < 1 || ngpus > SAB_MAX_DEVICES) {
+        sab_set_error("sab200_index_create: bad arguments");
+        return nullptr;
+    }
+    if (ngpus > sab200_device_count()) {
+        sab_set_error("sab200_index_create: %d GPUs requested, %d visible", (int)ngpus, (int)sab200_device_count());
+        return nullptr;
+    }
+    sab200_index* ix = new (std::nothrow) sab200_index();
+    if (!ix) return nullptr;
+    ix->n = n;
+    ix->has_bkt = bkt_or_null != nullptr;
+    ix->rep.resize(ngpus);
+    for (int d = 0; d < ngpus; ++d) {
+        if (replica_init(ix->rep[d], d, s, n, sa, bkt_or_null) != SAB_OK) {
+            for (auto& r : ix->rep) replica_free(r);
+            delete ix;
+            return nullptr;
+        }
+    }
+    return ix;
+}
+
+extern "C" void sab200_index_destroy(sab200_index* ix) {
+    if (!ix) return;
+    for (auto& r : ix->rep) replica_free(r);
+    delete ix;
+}
+
+template <int MODE>
+static int launch_search(SabReplica& r, u64 n, const u8* d_pats_adj, const u64* d_offs, u64 np, u32* d_out0, u32* d_out1) {
+    SearchArgs a;
+    a.text = r.d_text;
+    a.n = n;
+    a.sa = r.d_sa;
+    a.bkt = r.d_bkt;
+    a.pats = d_pats_adj;
+    a.offs = d_offs;
+    a.np = np;
+    a.out0 = d_out0;
+    a.out1 = d_out1;
+    const u64 threads = np * SAB_SEARCH_G;
+    SAB_LAUNCH((search_kernel<SAB_SEARCH_G, MODE>), (unsigned)div_up64(threads, SAB_SEARCH_THREADS), SAB_SEARCH_THREADS, 0,
+               r.ctx->stream, a);
+    SAB_LAUNCH_CHECK();
+    return SAB_OK;
+}
+
+static int replica_reserve(SabReplica& r, size_t pat_bytes, size_t np) {
+    if (r.pats_cap < pat_bytes + 64) {
+        cudaFree(r.d_pats);
+        r.d_pats = nullptr;
+        r.pats_cap = 0;
+        const size_t want = sab_align_up(pat_bytes + pat_bytes / 4 + 4096, 256);
+        SAB_CUDA_TRY(cudaMalloc(&r.d_pats, want));
+        SAB_CUDA_TRY(cudaMemset(r.d_pats, 0, want));
+        r.pats_cap = want;
+    }
+    if (r.np_cap < np + 1) {
+        cudaFree(r.d_offs);
+        cudaFree(r.d_out0);
+        cudaFree(r.d_out1);
+        r.d_offs = nullptr;
+        r.d_out0 = r.d_out1 = nullptr;
+        r.np_cap = 0;
+        const size_t want = np + np / 4 + 1024;
+        SAB_CUDA_TRY(cudaMalloc(&r.d_offs, want * sizeof(u64)));
+        SAB_CUDA_TRY(cudaMalloc(&r.d_out0, want * sizeof(u32)));
+        SAB_CUDA_TRY(cudaMalloc(&r.d_out1, want * sizeof(u32)));
+        r.np_cap = want;
+    }
+    return SAB_OK;
+}
+
+// mode 0 search_all (out0 = lo, out1 = hi), 1 contains (out0 = u8 flags), 2 search_lcp (start, end)
+static int search_batch(sab200_index* ix, int mode, const u8* pats, const u64* offs, u64 np, void* out0, void* out1) {
+    if (!ix || (np > 0 && (!offs || !out0)) || (mode != 1 && np > 0 && !out1)) {
+        sab_set_error("batched search: bad arguments");
+        return SAB_ERR_ARGS;
+    }
+    if (np == 0) return SAB_OK;
+    if (np > 0x7fffffffull) {
+        sab_set_error("batched search: at most 2^31-1 patterns per call");
+        return SAB_ERR_ARGS;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const int P = (int)ix->rep.size();
+    const u64 per = div_up64(np, (u64)P);
+    // enqueue on every replica, then drain
+    for (int d = 0; d < P; ++d) {
+        const u64 q0 = (u64)d * per, q1 = (q0 + per < np) ? q0 + per : np;
+        if (q0 >= q1) continue;
+        SabReplica& r = ix->rep[d];
+        SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
+        const u64 b0 = offs[q0], b1 = offs[q1];
+        const u64 cnt = q1 - q0;
+        SAB_TRY(replica_reserve(r, (size_t)(b1 - b0), (size_t)cnt));
+        cudaStream_t st = r.ctx->stream;
+        if (b1 > b0) SAB_CUDA_TRY(cudaMemcpyAsync(r.d_pats, pats + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        SAB_CUDA_TRY(cudaMemcpyAsync(r.d_offs, offs + q0, (cnt + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+        const u8* adj = r.d_pats - b0;  // the kernel indexes patterns by their absolute offsets
+        if (mode == 0) SAB_TRY(launch_search<0>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
+        else if (mode == 1) SAB_TRY(launch_search<1>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
+        else SAB_TRY(launch_search<2>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
+        if (mode == 1) {
+            SAB_CUDA_TRY(cudaMemcpyAsync((u8*)out0 + q0, r.d_out0, cnt, cudaMemcpyDeviceToHost, st));
+        } else {
+            SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out0 + q0, r.d_out0, cnt * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out1 + q0, r.d_out1, cnt * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int d = 0; d < P; ++d) {
+        SabReplica& r = ix->rep[d];
+        SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
+        SAB_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    }
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_search_all_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np, uint32_t* lo,
+                                uint32_t* hi) {
+    return search_batch(ix, 0, pats, offs, np, lo, hi);
+}
+extern "C" int32_t sab200_contains_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np, uint8_t* out) {
+    return search_batch(ix, 1, pats, offs, np, out, nullptr);
+}
+extern "C" int32_t sab200_search_lcp_batch(sab200_index* ix, const uint8_t* pats, const uint64_t* offs, uint64_t np,
+                                uint32_t* start, uint32_t* end) {
+    return search_batch(ix, 2, pats, offs, np, start, end);
+}
+
+// Device-resident variant for timing the kernel alone: d_pats / d_offs / d_lo / d_hi live on the
+// device of replica 0; d_pats must be followed by >= 8 readable bytes.
+extern "C" int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t np,
+                                       uint32_t* d_lo, uint32_t* d_hi) {
+    if (!ix || !d_offs || !d_lo || !d_hi) return SAB_ERR_ARGS;
+    if (np == 0) return SAB_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    SabReplica& r = ix->rep[0];
+    SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
+    SAB_TRY(launch_search<0>(r, ix->n, d_pats, d_offs, np, d_lo, d_hi));
+    SAB_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    return SAB_OK;
+}
+
+extern "C" {
 
 int32_t sab200_get_stats(sab200_stats* out) {
     if (!out) return SAB_ERR_ARGS;

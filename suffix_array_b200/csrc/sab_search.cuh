@@ -1,0 +1,304 @@
+// sab_search.cuh -- the query side of the hot path on the GPU:
+//   bucket_pairs / bucket_scan   enable_buckets            (/root/reference/src/sa.rs:89-119)
+//   search_kernel                get_bucket + search_all / contains / search_lcp, batched
+//                                (src/sa.rs:123-161, 164-170, 173-204, 207-253)
+//   sufcheck_*                   linear-time check_integrity (src/sa.rs:72-84)
+//
+// Each pattern is handled by a group of SAB_SEARCH_G lanes; a probe compares 4*G bytes of the
+// pattern with the suffix in one step (big-endian word compare + ballot).  The work is a chain
+// of dependent random reads (sa[mid], then text[sa[mid]..]): it is bound by the HBM random-
+// sector rate, not by arithmetic; many groups per SM keep enough probes in flight.
+#pragma once
+#include "sab_context.cuh"
+
+#define SAB_BKT_LEN 65793u
+#define SAB_SEARCH_G 8
+#define SAB_SEARCH_THREADS 256
+
+// ------------------------------------------------------------------ enable_buckets
+// Dense path: the byte pairs are counted in a shared table indexed by (code(c0), code'(c1)) of the
+// bytes present in the text; sparse path (large alphabets): global atomics straight into the table.
+// cnt[] has SAB_BKT_LEN u32 slots, zeroed by the caller; slot layout as in src/sa.rs:94,103,107.
+__global__ void __launch_bounds__(256)
+bucket_pairs_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, u32 sigma, int dense,
+                    u32* __restrict__ cnt) {
+    SAB_DYN_SMEM(smem);
+    u32* s_tab = (u32*)smem;  // [sigma][sigma+1]: column 0 = end-of-text, column c = code c (1..sigma)
+    SAB_SHARED_ARRAY(u16, s_lut, 256);
+    SAB_SHARED_ARRAY(u8, s_inv, 257);
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    if (s_lut[threadIdx.x]) s_inv[s_lut[threadIdx.x]] = (u8)threadIdx.x;
+    const u32 width = sigma + 1;
+    const u32 tab = sigma * width;
+    if (dense)
+        for (u32 i = threadIdx.x; i < tab; i += blockDim.x) s_tab[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 c0 = text[i];
+        if (dense) {
+            const u32 col = (i + 1 < n) ? (u32)s_lut[text[i + 1]] : 0u;
+            atomicAdd(&s_tab[((u32)s_lut[c0] - 1u) * width + col], 1u);
+        } else {
+            const u32 slot = (i + 1 < n) ? c0 * 257u + (u32)text[i + 1] + 2u : c0 * 257u + 1u;
+            atomicAdd(&cnt[slot], 1u);
+        }
+    }
+    __syncthreads();
+    if (dense)
+        for (u32 i = threadIdx.x; i < tab; i += blockDim.x) {
+            const u32 v = s_tab[i];
+            if (v) {
+                const u32 r = i / width, col = i % width;
+                const u32 c0 = s_inv[r + 1];
+                const u32 slot = col ? c0 * 257u + (u32)s_inv[col] + 2u : c0 * 257u + 1u;
+                atomicAdd(&cnt[slot], v);
+            }
+        }
+}
+
+// inclusive prefix sum of the 65 793 counters (u32 wrap-around as in src/sa.rs:112-116); bkt[0] += 1
+// accounts for the empty suffix (src/sa.rs:98).  One block of 1024 threads.
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(u32* __restrict__ bkt) {
+    SAB_SHARED_ARRAY(u32, s_w, 32);
+    constexpr u32 PER = (SAB_BKT_LEN + 1023u) / 1024u;  // 65
+    const u32 t = threadIdx.x, lane = lane_id(), w = warp_id();
+    const u32 b0 = t * PER;
+    u32 sum = 0;
+    for (u32 i = 0; i < PER; ++i) {
+        const u32 j = b0 + i;
+        if (j < SAB_BKT_LEN) sum += bkt[j] + (j == 0 ? 1u : 0u);
+    }
+    u32 incl = warp_incl_sum(sum);
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        u32 v = s_w[lane];
+        v = warp_incl_sum(v);
+        s_w[lane] = v;
+    }
+    __syncthreads();
+    u32 run = incl - sum + (w ? s_w[w - 1] : 0u);
+    for (u32 i = 0; i < PER; ++i) {
+        const u32 j = b0 + i;
+        if (j < SAB_BKT_LEN) {
+            run += bkt[j] + (j == 0 ? 1u : 0u);
+            bkt[j] = run;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ batched queries
+// 4 bytes at byte offset `off` of `base`, first byte in the most significant position.  Reads the
+// two aligned words covering them: buffers are padded by >= 8 readable bytes.
+__device__ __forceinline__ u32 load_be32(const u8* __restrict__ base, u64 off) {
+    const uintptr_t a = (uintptr_t)(base + off);
+    const u32* w = (const u32*)(a & ~(uintptr_t)3);
+    const u32 sh = (u32)(a & 3u) * 8u;
+    const u32 lo = w[0];
+    const u32 hi = sh ? w[1] : 0u;
+    const u32 v = __funnelshift_r(lo, hi, sh);
+    return __byte_perm(v, 0u, 0x0123u);
+}
+
+struct SearchArgs {
+    const u8* text;   // n bytes (+ padding)
+    u64 n;
+    const u32* sa;    // n + 1
+    const u32* bkt;   // SAB_BKT_LEN or null
+    const u8* pats;   // concatenated patterns (+ padding)
+    const u64* offs;  // np + 1
+    u64 np;
+    u32* out0;        // search_all: lo   | search_lcp: start | contains: (u8*) flags
+    u32* out1;        // search_all: hi   | search_lcp: end
+};
+
+// Compares pattern (pat, m) with the suffix at p.  Returns d = length of their common prefix
+// (<= L = min(m, n - p)); *less_at = 1 when d < L and text[p+d] < pat[d].
+template <int G>
+__device__ __forceinline__ u64 group_compare(const SearchArgs& a, const u8* __restrict__ pat, u64 m, u64 p, u32 gmask,
+                                             u32 gl, u32 gbase, u32 pw0, u32 pw1, u32* less_at) {
+    const u64 avail = a.n - p;
+    const u64 L = m < avail ? m : avail;
+    *less_at = 0;
+    for (u64 c0 = 0; c0 < L || c0 == 0; c0 += 4 * G) {
+        const u64 o = c0 + 4u * gl;
+        u32 neq = 0, tw = 0, pw = 0;
+        if (o < L) {
+            const u64 rem = L - o;
+            const u32 mask = rem >= 4 ? 0xffffffffu : (0xffffffffu << (8u * (4u - (u32)rem)));
+            tw = load_be32(a.text, p + o) & mask;
+            pw = (c0 == 0 ? pw0 : (c0 == 4 * G ? pw1 : load_be32(pat, o))) & mask;
+            neq = tw ^ pw;
+        }
+        const u32 bal = (__ballot_sync(gmask, neq != 0) >> gbase) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+        if (bal) {
+            const int first = __ffs((int)bal) - 1;
+            const u32 fneq = __shfl_sync(gmask, neq, (int)gbase + first);
+            const u32 fless = __shfl_sync(gmask, (u32)(tw < pw), (int)gbase + first);
+            *less_at = fless;
+            return c0 + 4u * (u32)first + (u32)(__clz((int)fneq) >> 3);
+        }
+        if (L == 0) break;
+    }
+    return L;
+}
+
+// MODE 0: search_all -> [lo, hi) global SA indices;  1: contains -> u8;  2: search_lcp -> [start, end)
+template <int G, int MODE>
+__global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a) {
+    const u64 gtid = (u64)blockIdx.x * SAB_SEARCH_THREADS + threadIdx.x;
+    const u64 q = gtid / G;
+    if (q >= a.np) return;
+    const u32 lane = lane_id();
+    const u32 gl = lane % G, gbase = lane - gl;
+    const u32 gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const u64 pbeg = a.offs[q];
+    const u64 m = a.offs[q + 1] - pbeg;
+    const u8* pat = a.pats + pbeg;
+    const u64 n = a.n;
+    // pattern words of the first two probe chunks stay in registers
+    const u32 pw0 = (4u * gl < m) ? load_be32(pat, 4u * gl) : 0u;
+    const u32 pw1 = (4u * G + 4u * gl < m) ? load_be32(pat, 4u * G + 4u * gl) : 0u;
+
+    // get_bucket (src/sa.rs:123-144); MODE 0 with an empty pattern searches the whole array (:175-179)
+    u64 lo = 0, hi = n + 1;
+    if (a.bkt) {
+        if (m > 1) {
+            const u32 idx = (u32)pat[0] * 257u + (u32)pat[1] + 2u;
+            lo = a.bkt[idx - 1];
+            hi = a.bkt[idx];
+        } else if (m == 1) {
+            const u32 st = (u32)pat[0] * 257u;
+            lo = a.bkt[st];
+            hi = a.bkt[st + 257];
+        } else if (MODE != 0) {
+            lo = 0;
+            hi = 1;
+        }
+    }
+    if (MODE == 2 && hi == lo) {  // src/sa.rs:211-222 (only reachable with buckets and m > 0)
+        const u32 st = (u32)pat[0] * 257u;
+        const u64 tl = a.bkt[st], th = a.bkt[st + 257];
+        if (gl == 0) {
+            if (th > tl) {
+                const u32 i = a.sa[tl];
+                a.out0[q] = i;
+                a.out1[q] = i + 1u;
+            } else {
+                a.out0[q] = (u32)n;
+                a.out1[q] = (u32)n;
+            }
+        }
+        return;
+    }
+    // lower bound: first index whose suffix is not < pat   (src/sa.rs:181-190)
+    u64 i = lo, k = hi;
+    while (i < k) {
+        const u64 mid = i + (k - i) / 2;
+        const u64 p = a.sa[mid];
+        u32 less_at;
+        const u64 d = group_compare<G>(a, pat, m, p, gmask, gl, gbase, pw0, pw1, &less_at);
+        const u64 avail = n - p;
+        const u64 L = m < avail ? m : avail;
+        const bool suffix_less = (d < L) ? (less_at != 0) : (avail < m);
+        if (suffix_less) i = mid + 1;
+        else k = mid;
+    }
+    if (MODE == 0) {
+        // upper bound: first index >= i whose suffix does not start with pat   (src/sa.rs:192-201)
+        u64 j = i;
+        k = hi;
+        while (j < k) {
+            const u64 mid = j + (k - j) / 2;
+            const u64 p = a.sa[mid];
+            u32 less_at;
+            const u64 d = group_compare<G>(a, pat, m, p, gmask, gl, gbase, pw0, pw1, &less_at);
+            if (d == m) j = mid + 1;
+            else k = mid;
+        }
+        if (gl == 0) {
+            a.out0[q] = (u32)i;
+            a.out1[q] = (u32)j;
+        }
+    } else if (MODE == 1) {
+        // src/sa.rs:168-169: a suffix whose truncation equals pat exists iff the lower bound starts with pat
+        bool found = false;
+        if (i < hi) {
+            u32 less_at;
+            found = group_compare<G>(a, pat, m, a.sa[i], gmask, gl, gbase, pw0, pw1, &less_at) == m;
+        }
+        if (gl == 0) ((u8*)a.out0)[q] = found ? 1 : 0;
+    } else {
+        // src/sa.rs:224-252
+        u32 less_at;
+        u64 st = 0, en = 0;
+        u64 pb = 0, db = 0;
+        if (i < hi) {
+            pb = a.sa[i];
+            db = group_compare<G>(a, pat, m, pb, gmask, gl, gbase, pw0, pw1, &less_at);
+        }
+        if (i < hi && db == m && n - pb == m) {  // Ok(i): a suffix equal to the pattern
+            st = pb;
+            en = n;
+        } else if (i > lo && i < hi) {
+            const u64 pa = a.sa[i - 1];
+            const u64 da = group_compare<G>(a, pat, m, pa, gmask, gl, gbase, pw0, pw1, &less_at);
+            if (da > db) {
+                st = pa;
+                en = pa + da;
+            } else {
+                st = pb;
+                en = pb + db;
+            }
+        } else if (i == lo) {
+            st = pb;
+            en = pb + db;
+        } else {
+            const u64 pa = a.sa[i - 1];
+            const u64 da = group_compare<G>(a, pat, m, pa, gmask, gl, gbase, pw0, pw1, &less_at);
+            st = pa;
+            en = pa + da;
+        }
+        if (gl == 0) {
+            a.out0[q] = (u32)st;
+            a.out1[q] = (u32)en;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ linear-time integrity check
+// flags[0] != 0 -> not a suffix array.  isa must be pre-filled with 0xFFFFFFFF.
+__global__ void __launch_bounds__(256)
+sufcheck_scatter_kernel(const u32* __restrict__ sa, u64 len, u64 n, u32* __restrict__ isa, u32* __restrict__ flags) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const u32 v = sa[j];
+    if ((u64)v > n || (j == 0 && (u64)v != n)) {
+        flags[0] = 1;
+        return;
+    }
+    isa[v] = (u32)j;
+}
+
+__global__ void __launch_bounds__(256)
+sufcheck_order_kernel(const u8* __restrict__ text, const u32* __restrict__ sa, u64 len, u64 n,
+                      const u32* __restrict__ isa, u32* __restrict__ flags) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    const u32 b = sa[j];
+    if ((u64)b > n) return;  // already flagged
+    if (isa[b] != (u32)j) {  // duplicate entry somewhere -> not a permutation
+        flags[0] = 1;
+        return;
+    }
+    if (j < 2) return;  // sa[0] = n was checked; sa[1] follows the empty suffix
+    const u32 x = sa[j - 1];
+    if ((u64)x >= n || (u64)b >= n) {
+        flags[0] = 1;  // the empty suffix anywhere but in front
+        return;
+    }
+    const u8 cx = text[x], cb = text[b];
+    if (cx > cb || (cx == cb && isa[x + 1] >= isa[b + 1])) flags[0] = 1;
+}

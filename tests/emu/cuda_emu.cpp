@@ -49,10 +49,11 @@ struct Fiber {
     void* sp;
     int state;
     int tid;
+    unsigned wait_mask;  // lanes this fiber rendezvouses with (AT_WARP)
 };
 struct WarpState {
     uint64_t slots[32];
-    int arrived;
+    unsigned arrived;  // bit per lane waiting at a warp rendezvous
     unsigned live;
 };
 struct SharedVar {
@@ -112,10 +113,36 @@ void sync_block() {
     g_block->at_block++;
     to_scheduler();
 }
-void sync_warp() {
+void sync_warp(unsigned mask) {
     g_fiber->state = AT_WARP;
-    g_block->warps[g_fiber->tid >> 5].arrived++;
+    g_fiber->wait_mask = mask;
+    g_block->warps[g_fiber->tid >> 5].arrived |= 1u << (g_fiber->tid & 31);
     to_scheduler();
+}
+// release every group of lanes whose members (still alive) have all arrived with the same mask
+static bool release_warp(Block& b, int w) {
+    WarpState& ws = b.warps[w];
+    bool any = false;
+    unsigned pending = ws.arrived;
+    while (pending) {
+        const int lane = __builtin_ctz(pending);
+        Fiber& f = b.fibers[w * 32 + lane];
+        const unsigned need = f.wait_mask & ws.live;
+        pending &= ~need;
+        pending &= ~(1u << lane);
+        if ((ws.arrived & need) != need) continue;
+        bool same = true;
+        for (unsigned m = need; m; m &= m - 1)
+            if (b.fibers[w * 32 + __builtin_ctz(m)].wait_mask != f.wait_mask) same = false;
+        if (!same) {
+            fprintf(stderr, "emu: lanes of one warp collective disagree on the member mask\n");
+            abort();
+        }
+        for (unsigned m = need; m; m &= m - 1) b.fibers[w * 32 + __builtin_ctz(m)].state = RUNNABLE;
+        ws.arrived &= ~need;
+        any = true;
+    }
+    return any;
 }
 uint64_t* warp_slots() { return g_block->warps[g_fiber->tid >> 5].slots; }
 uint32_t warp_live_mask() { return g_block->warps[g_fiber->tid >> 5].live; }
@@ -227,13 +254,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
                     progressed = true;
                 }
                 // warp rendezvous release
-                WarpState& ws = b.warps[w];
-                if (ws.arrived > 0 && ws.arrived == __builtin_popcount(ws.live)) {
-                    ws.arrived = 0;
-                    for (int t = w * 32; t < nt && t < w * 32 + 32; ++t)
-                        if (b.fibers[t].state == AT_WARP) b.fibers[t].state = RUNNABLE;
-                    progressed = true;
-                }
+                if (b.warps[w].arrived && release_warp(b, w)) progressed = true;
             }
             if (b.live > 0 && b.at_block == b.live) {
                 b.at_block = 0;
@@ -242,14 +263,8 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
                 progressed = true;
             }
             // an exiting lane can complete a warp rendezvous of the remaining lanes
-            for (auto& ws : b.warps)
-                if (ws.arrived > 0 && ws.arrived == __builtin_popcount(ws.live)) {
-                    int w = (int)(&ws - &b.warps[0]);
-                    ws.arrived = 0;
-                    for (int t = w * 32; t < nt && t < w * 32 + 32; ++t)
-                        if (b.fibers[t].state == AT_WARP) b.fibers[t].state = RUNNABLE;
-                    progressed = true;
-                }
+            for (int w = 0; w < (int)b.warps.size(); ++w)
+                if (b.warps[w].arrived && release_warp(b, w)) progressed = true;
             if (b.live == 0) {
                 finish_block(b);
                 used[s] = 0;

@@ -53,7 +53,7 @@ namespace emu {
 void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);
 void yield_spin();                 // a thread spinning on global memory lets others run
 void sync_block();                 // __syncthreads
-void sync_warp();                  // warp rendezvous (all live lanes of the warp)
+void sync_warp(unsigned mask);     // rendezvous of the live lanes named by mask
 void* shared_get(const void* key, size_t bytes);
 void* dyn_smem();
 uint64_t* warp_slots();            // 32 exchange slots of the calling thread's warp
@@ -71,7 +71,7 @@ void set_window(int resident_blocks);
 
 // ------------------------------------------------------------------ intrinsics
 static inline void __syncthreads() { emu::sync_block(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync_warp(); }
+static inline void __syncwarp(unsigned m = 0xffffffffu) { emu::sync_warp(m); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline unsigned __activemask() { return emu::warp_live_mask(); }
@@ -117,47 +117,47 @@ static inline T emu_from_bits(uint64_t b) {
 }
 // every collective: deposit, rendezvous, compute, rendezvous
 template <typename F>
-static inline auto emu_collective(uint64_t mine, F f) -> decltype(f((const uint64_t*)0, 0u, 0)) {
+static inline auto emu_collective(unsigned mask, uint64_t mine, F f) -> decltype(f((const uint64_t*)0, 0u, 0)) {
     uint64_t* slots = emu::warp_slots();
     int lane = (int)(threadIdx.x & 31);
     slots[lane] = mine;
-    emu::sync_warp();
-    auto r = f((const uint64_t*)slots, emu::warp_live_mask(), lane);
-    emu::sync_warp();
+    emu::sync_warp(mask);
+    auto r = f((const uint64_t*)slots, emu::warp_live_mask() & mask, lane);
+    emu::sync_warp(mask);
     return r;
 }
 template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
-    return emu_collective(emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    return emu_collective(mask, emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
         int base = lane & ~(width - 1);
         return emu_from_bits<T>(s[base + (src & (width - 1))]);
     });
 }
 template <typename T>
-static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
-    return emu_collective(emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
+    return emu_collective(mask, emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
         int base = lane & ~(width - 1);
         int src = lane - (int)d;
         return emu_from_bits<T>(s[src < base ? lane : src]);
     });
 }
 template <typename T>
-static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
-    return emu_collective(emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
+static inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
+    return emu_collective(mask, emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
         int base = lane & ~(width - 1);
         int src = lane + (int)d;
         return emu_from_bits<T>(s[src >= base + width ? lane : src]);
     });
 }
 template <typename T>
-static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
+static inline T __shfl_xor_sync(unsigned mask, T v, int m, int width = 32) {
     (void)width;
-    return emu_collective(emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
+    return emu_collective(mask, emu_to_bits(v), [&](const uint64_t* s, unsigned, int lane) {
         return emu_from_bits<T>(s[(lane ^ m) & 31]);
     });
 }
-static inline unsigned __ballot_sync(unsigned, int pred) {
-    return emu_collective(pred ? 1u : 0u, [&](const uint64_t* s, unsigned live, int) {
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    return emu_collective(mask, pred ? 1u : 0u, [&](const uint64_t* s, unsigned live, int) {
         unsigned r = 0;
         for (int i = 0; i < 32; ++i)
             if (((live >> i) & 1u) && s[i]) r |= 1u << i;
@@ -165,26 +165,26 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     });
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
-static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == emu::warp_live_mask(); }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == (emu::warp_live_mask() & m); }
 template <typename T>
-static inline unsigned __match_any_sync(unsigned, T v) {
-    return emu_collective(emu_to_bits(v), [&](const uint64_t* s, unsigned live, int lane) {
+static inline unsigned __match_any_sync(unsigned mask, T v) {
+    return emu_collective(mask, emu_to_bits(v), [&](const uint64_t* s, unsigned live, int lane) {
         unsigned r = 0;
         for (int i = 0; i < 32; ++i)
             if (((live >> i) & 1u) && s[i] == s[lane]) r |= 1u << i;
         return r;
     });
 }
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
-    return emu_collective((uint64_t)v, [&](const uint64_t* s, unsigned live, int) {
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    return emu_collective(mask, (uint64_t)v, [&](const uint64_t* s, unsigned live, int) {
         unsigned r = 0;
         for (int i = 0; i < 32; ++i)
             if ((live >> i) & 1u) r += (unsigned)s[i];
         return r;
     });
 }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
-    return emu_collective((uint64_t)v, [&](const uint64_t* s, unsigned live, int) {
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    return emu_collective(mask, (uint64_t)v, [&](const uint64_t* s, unsigned live, int) {
         unsigned r = 0;
         for (int i = 0; i < 32; ++i)
             if (((live >> i) & 1u) && (unsigned)s[i] > r) r = (unsigned)s[i];

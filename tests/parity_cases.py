@@ -1,0 +1,148 @@
+"""Parity checks shared by the GPU tests (tests/test_gpu_*.py, through libsab200.so on a B200) and
+the CPU-only kernel-logic tests (tests/test_emu_*.py, same CUDA sources under the SIMT emulator).
+Every check compares the engine with the oracle (bit-exact) on the same input."""
+import numpy as np
+
+from suffix_array_b200 import SuffixArray, gen
+
+
+def adversarial_texts():
+    """all-equal bytes, 0x00 runs, period-2, Fibonacci / Thue-Morse, n around 128."""
+    def fib(k):
+        a, b = b"b", b"a"
+        for _ in range(k):
+            a, b = b, b + a
+        return b
+    tm = bytes((bin(i).count("1") & 1) + 97 for i in range(1 << 10))
+    out = [b"", b"\x00", b"\x00\x00\x00", b"a\x00", b"\x00a", b"\xff", b"\xff\xff", b"ab" * 300, b"a" * 127, b"a" * 128,
+           b"a" * 129, b"a" * 1000, b"\x00" * 777, fib(14), tm, bytes(range(256)) * 3, b"abc" * 500 + b"abd",
+           b"\xff\x00" * 200 + b"\xff"]
+    return [np.frombuffer(t, dtype=np.uint8) for t in out]
+
+
+def check_construction(oracle, s):
+    s = np.ascontiguousarray(s, dtype=np.uint8)
+    sa = SuffixArray(s)
+    got = sa.into_parts()[1]
+    exp = oracle.saca(s)
+    assert got.dtype == np.uint32 and got.size == s.size + 1
+    assert np.array_equal(got, exp), "suffix array differs from the oracle (n=%d)" % s.size
+    return got
+
+
+def check_golden(oracle, golden):
+    for v in golden["vectors"]:
+        s = np.frombuffer(bytes.fromhex(v["text_hex"]), dtype=np.uint8)
+        sa = SuffixArray(s)
+        assert sa.sa.tolist() == v["sa"]
+        for with_bkt in (False, True):
+            if with_bkt:
+                sa.enable_buckets()
+                steps, prev = {}, 0
+                for i, x in enumerate(sa.bkt.tolist()):
+                    if x != prev:
+                        steps[str(i)] = x
+                        prev = x
+                assert steps == v["bkt_steps"]
+            pats = [bytes.fromhex(q["pat_hex"]) for q in v["queries"]]
+            lo, hi = sa.search_all_batch(pats)
+            cont = sa.contains_batch(pats)
+            st, en = sa.search_lcp_batch(pats)
+            for k, q in enumerate(v["queries"]):
+                assert [int(lo[k]), int(hi[k])] == q["range"], (v["text_hex"][:32], q["pat_hex"], with_bkt)
+                assert bool(cont[k]) == q["contains"]
+                assert int(en[k]) - int(st[k]) == q["lcp_len"]
+                assert bytes(s[int(st[k]):int(en[k])]) == pats[k][:q["lcp_len"]]
+
+
+def check_doctests(golden):
+    d = golden["doctests"]  # /root/reference/src/lib.rs:19-40
+    s = d["text"].encode()
+    sa = SuffixArray.new(s)
+    assert sa.contains(d["contains"][0].encode()) is True
+    assert sa.search_all(d["search_all"][0].encode()).tolist() == d["search_all"][1]
+    r = sa.search_lcp(d["search_lcp"][0].encode())
+    assert s[r.start:r.stop] == d["search_lcp"][1].encode()
+
+
+def random_patterns(rng, s, count, max_len=40):
+    """the three schemes of src/tests.rs:79-102"""
+    n = s.size
+    pats = []
+    for _ in range(count):
+        m = int(rng.integers(0, min(max_len, n) + 1))
+        kind = int(rng.integers(0, 3))
+        if kind == 0 or n == 0:
+            i = int(rng.integers(0, n - m + 1))
+            p = s[i:i + m].tobytes()
+        elif kind == 1:
+            i = int(rng.integers(0, n - m + 1))
+            j = int(rng.integers(0, m + 1))
+            p = s[i:i + m - j].tobytes() + rng.integers(0, 256, j, dtype=np.uint8).tobytes()
+        else:
+            p = rng.integers(0, 256, m, dtype=np.uint8).tobytes()
+        pats.append(p)
+    return pats
+
+
+def check_queries(oracle, s, pats, ngpus=1):
+    """search_all / contains / search_lcp, without and with buckets, against the literal oracle."""
+    s = np.ascontiguousarray(s, dtype=np.uint8)
+    sa = SuffixArray(s)
+    sa.use_gpus(ngpus)
+    exp_sa = oracle.saca(s)
+    assert np.array_equal(sa.sa, exp_sa)
+    flat = np.frombuffer(b"".join(pats), dtype=np.uint8)
+    offs = np.zeros(len(pats) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(p) for p in pats])
+    for with_bkt in (False, True):
+        bkt = None
+        if with_bkt:
+            sa.enable_buckets()
+            bkt = oracle.enable_buckets(s)
+            assert np.array_equal(sa.bkt, bkt), "bucket table differs"
+        lo, hi = sa.search_all_batch(flat, offs)
+        elo, ehi = oracle.search_all_batch(s, exp_sa, bkt, flat, offs)
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi), "search_all ranges differ (buckets=%s)" % with_bkt
+        assert np.array_equal(sa.contains_batch(flat, offs), oracle.contains_batch(s, exp_sa, bkt, flat, offs))
+        st, en = sa.search_lcp_batch(flat, offs)
+        est, een = oracle.search_lcp_batch(s, exp_sa, bkt, flat, offs)
+        assert np.array_equal(st, est) and np.array_equal(en, een), "search_lcp ranges differ (buckets=%s)" % with_bkt
+    return sa
+
+
+def check_from_parts(oracle, s):
+    s = np.ascontiguousarray(s, dtype=np.uint8)
+    good = oracle.saca(s)
+    assert SuffixArray.from_parts(s, good) is not None
+    assert SuffixArray.from_parts(s, good[:-1]) is None  # src/sa.rs:73-75
+    if s.size >= 2:
+        rng = np.random.default_rng(s.size)
+        bad = good.copy()
+        i = int(rng.integers(1, s.size))
+        bad[i], bad[i + 1] = bad[i + 1], bad[i]
+        assert SuffixArray.from_parts(s, bad) is None
+        dup = good.copy()
+        dup[i] = dup[i + 1]
+        assert SuffixArray.from_parts(s, dup) is None
+        oob = good.copy()
+        oob[i] = s.size + 5
+        assert SuffixArray.from_parts(s, oob) is None
+        rot = np.roll(good, 1)
+        assert SuffixArray.from_parts(s, rot) is None
+
+
+def sampled_order_check(s, sa, samples=200000, seed=0):
+    """Size-independent property for texts too big for the O(n) CPU verifier to be quick:
+    sa is a permutation (checksum + bitmap on a sample) and sampled neighbours are in strict order."""
+    n = s.size
+    assert sa.size == n + 1 and int(sa[0]) == n
+    assert int(sa.astype(np.uint64).sum()) == n * (n + 1) // 2
+    rng = np.random.default_rng(seed)
+    js = rng.integers(1, n + 1, min(samples, n))
+    tb = s.tobytes() if n <= (1 << 28) else None
+    for j in js[:2000] if tb is None else js[:20000]:
+        a, b = int(sa[j - 1]), int(sa[j])
+        x = (tb[a:a + 4096] if tb is not None else s[a:a + 4096].tobytes())
+        y = (tb[b:b + 4096] if tb is not None else s[b:b + 4096].tobytes())
+        assert x < y or (x == y and len(x) == 4096), (int(j), a, b)

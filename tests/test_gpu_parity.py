@@ -1,0 +1,146 @@
+"""Parity gate: libsab200.so on a B200 against the oracle, through the C ABI (host mirror
+suffix_array_b200.SuffixArray -> include/sab200.h).  Bit-exact on every input.
+
+Mirrors the reference's own tests (/root/reference/src/tests.rs:12-59: conversion, contains,
+search_all, search_lcp, each without and with enable_buckets; texts any::<u8>() of 0..4096 bytes)
+and adds the adversarial and BASELINE.json-shaped inputs of SURVEY.md section 4."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+from suffix_array_b200 import SuffixArray, gen
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_loaded(gpu_lib):
+    import suffix_array_b200._lib as L
+    assert b"sm_100a" in gpu_lib.sab200_version()
+    with open("/proc/self/maps") as f:
+        assert "libsab200.so" in f.read()
+    assert L.lib().sab200_device_count() >= 1
+
+
+def test_golden_and_doctests(gpu_lib, oracle, golden):
+    pc.check_golden(oracle, golden)
+    pc.check_doctests(golden)
+
+
+def test_adversarial(gpu_lib, oracle):
+    for s in pc.adversarial_texts():
+        pc.check_construction(oracle, s)
+        pc.check_from_parts(oracle, s)
+
+
+@st.composite
+def bytes_with_pat(draw, max_size):
+    s = draw(st.binary(min_size=0, max_size=max_size))
+    n = len(s)
+    m = int(n * draw(st.floats(min_value=0.0, max_value=0.999)))
+    kind = draw(st.integers(0, 2))
+    if kind == 0:
+        i = draw(st.integers(0, n - m))
+        return s, s[i:i + m]
+    if kind == 1:
+        i = draw(st.integers(0, n - m))
+        junk = draw(st.binary(min_size=0, max_size=m))
+        return s, s[i:i + (m - len(junk))] + junk
+    return s, draw(st.binary(min_size=m, max_size=m))
+
+
+_hyp = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                   HealthCheck.function_scoped_fixture])
+
+
+@settings(max_examples=120, **_hyp)
+@given(st.binary(min_size=0, max_size=4096))
+def test_conversion_correctness(gpu_lib, oracle, s):
+    # src/tests.rs:14-17: new(s).into_parts() -> from_parts must be Some; plus bit-exact vs oracle
+    t, sa = SuffixArray.new(s).into_parts()
+    assert SuffixArray.from_parts(t, sa) is not None
+    assert oracle.check_integrity(s, sa)
+    assert np.array_equal(sa, oracle.saca(s))
+
+
+@settings(max_examples=120, **_hyp)
+@given(bytes_with_pat(4096))
+def test_query_correctness(gpu_lib, oracle, sp):
+    # src/tests.rs:20-59: contains / search_all / search_lcp vs the naive checkers, without and with buckets
+    s, pat = sp
+    sa = SuffixArray.new(s)
+    nc = oracle.naive_contains(s, pat)
+    na = np.sort(oracle.naive_search_all(s, pat))
+    nl = oracle.naive_search_lcp(s, pat)
+    for with_bkt in (False, True):
+        if with_bkt:
+            sa.enable_buckets()
+        assert sa.contains(pat) == nc
+        assert np.array_equal(np.sort(sa.search_all(pat)), na)
+        r = sa.search_lcp(pat)
+        assert s[r.start:r.stop] == pat[:nl]
+
+
+def test_random_mid_sizes(gpu_lib, oracle):
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(0, 300000))
+        sigma = int(rng.choice([1, 2, 3, 4, 5, 16, 100, 256]))
+        s = rng.integers(0, sigma, n, dtype=np.uint8)
+        if trial % 3 == 0 and n > 100:
+            p = int(rng.integers(1, 5000))
+            s = np.tile(s[:p], n // p + 1)[:n].copy()
+            s[int(rng.integers(0, n))] ^= 1
+        pc.check_construction(oracle, s)
+
+
+def test_queries_vs_oracle(gpu_lib, oracle):
+    rng = np.random.default_rng(99)
+    for sigma, n in ((4, 200000), (256, 100000), (2, 5000), (1, 700), (20, 50000)):
+        s = rng.integers(0, sigma, n, dtype=np.uint8)
+        pats = pc.random_patterns(rng, s, 3000, max_len=200) + [b"", s[:1].tobytes(), s[-1:].tobytes(), s[:5000].tobytes()]
+        pc.check_queries(oracle, s, pats)
+    pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
+
+
+def test_baseline_shapes_16mib_bit_exact(gpu_lib, oracle):
+    # the named shapes at a size the oracle finishes in seconds: bit-exact
+    n = 16 << 20
+    for s in (gen.uniform_bytes(n), gen.dna_like(n), gen.repetitive(n, block=1 << 16), gen.mixed(n)):
+        pc.check_construction(oracle, s)
+
+
+def test_c1_uniform_64mib(gpu_lib, oracle):
+    # BASELINE.json configs[0] at full size: linear-time verifiers on CPU and GPU
+    s = gen.uniform_bytes(64 << 20)
+    sa = SuffixArray(s)
+    assert oracle.sufcheck(s, sa.sa)
+    assert SuffixArray.from_parts(s, sa.sa) is not None
+
+
+def test_c3_repetitive_256mib(gpu_lib, oracle):
+    # BASELINE.json configs[2] at full size (long LCPs, ~14 doubling rounds)
+    s = gen.repetitive(256 << 20)
+    sa = SuffixArray(s)
+    assert SuffixArray.from_parts(s, sa.sa) is not None      # GPU linear-time check (a6 semantics)
+    pc.sampled_order_check(s, sa.sa)
+    # stress variants (correctness only): pure periodic and all-equal
+    for t in (gen.repetitive(8 << 20, block=1 << 12, mut_rate=0.0), np.full(4 << 20, ord("a"), dtype=np.uint8)):
+        pc.check_construction(oracle, t)
+
+
+def test_c2_dna_1gib(gpu_lib, oracle):
+    # BASELINE.json configs[1] at full size: GPU verifier + checksum + sampled neighbour order on CPU,
+    # and a bit-exact diff of a 64 MiB prefix-text run against the oracle's verifier
+    s = gen.dna_like(1 << 30)
+    sa = SuffixArray(s)
+    assert SuffixArray.from_parts(s, sa.sa) is not None
+    pc.sampled_order_check(s, sa.sa)
+    # search on the finished 1 GiB index (C5 shape, reduced pattern count): exact (lo, hi) / bool
+    sa.enable_buckets()
+    pats, offs = gen.patterns(s, 20000)
+    lo, hi = sa.search_all_batch(pats, offs)
+    elo, ehi = oracle.search_all_batch(s, sa.sa, sa.bkt, pats, offs)
+    assert np.array_equal(lo, elo) and np.array_equal(hi, ehi)
+    assert np.array_equal(sa.contains_batch(pats, offs), oracle.contains_batch(s, sa.sa, sa.bkt, pats, offs))
+    assert np.array_equal(sa.bkt, oracle.enable_buckets(s))
