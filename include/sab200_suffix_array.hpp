@@ -1,0 +1,158 @@
+// sab200_suffix_array.hpp -- C++ host mirror of the reference's `SuffixArray`
+// (/root/reference/src/sa.rs:14-374) over the C ABI of sab200.h.
+//
+// The reference is a Rust crate and this image has no Rust toolchain, so the compiled-language host
+// above the C ABI is C++ (header-only).  Same method names, argument meaning and error behaviour:
+//   * construction asserts like saca() (src/saca.rs:10-11) -> std::length_error / std::runtime_error
+//   * from_parts returns std::nullopt where the reference returns None (src/sa.rs:57-64)
+//   * search_all returns a (pointer, length) view into the suffix array, SA order (src/sa.rs:203)
+//   * search_lcp returns the half-open text range (src/sa.rs:207)
+// Per-pattern queries go through the batched GPU entry points with a batch of one; the *_batch
+// methods are the intended fast path.  No method has a CPU fallback.
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "sab200.h"
+
+namespace sab200 {
+
+constexpr std::size_t MAX_LENGTH = SAB200_MAX_LENGTH;  // replaces src/saca.rs:6
+
+struct Slice {
+    const std::uint32_t* data;
+    std::size_t len;
+    const std::uint32_t* begin() const { return data; }
+    const std::uint32_t* end() const { return data + len; }
+};
+struct Range {
+    std::size_t start, end;
+};
+
+inline void check(std::int32_t rc, const char* what) {
+    if (rc != SAB200_OK) throw std::runtime_error(std::string(what) + ": " + sab200_last_error());
+}
+
+// src/saca.rs:9-15
+inline void saca(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t>& sa, int ngpus = 1) {
+    if (n > MAX_LENGTH) throw std::length_error("text longer than MAX_LENGTH");  // :10
+    if (sa.size() != n + 1) throw std::length_error("sa.len() != s.len() + 1");   // :11
+    check(sab200_saca(s, n, sa.data(), ngpus), "sab200_saca");
+}
+
+class SuffixArray {
+  public:
+    // src/sa.rs:23-27
+    SuffixArray(const std::uint8_t* s, std::size_t n) : s_(s), n_(n), sa_(n + 1, 0) { saca(s_, n_, sa_); }
+    static SuffixArray make(const std::uint8_t* s, std::size_t n) { return SuffixArray(s, n); }
+    ~SuffixArray() { drop_index(); }
+    SuffixArray(SuffixArray&& o) noexcept
+        : s_(o.s_), n_(o.n_), sa_(std::move(o.sa_)), bkt_(std::move(o.bkt_)), has_bkt_(o.has_bkt_), ix_(o.ix_) {
+        o.ix_ = nullptr;
+    }
+    SuffixArray(const SuffixArray& o) : s_(o.s_), n_(o.n_), sa_(o.sa_), bkt_(o.bkt_), has_bkt_(o.has_bkt_) {}  // #[derive(Clone)]
+    SuffixArray& operator=(const SuffixArray&) = delete;
+
+    // src/sa.rs:30-33, literally: the stored text and the bucket table are NOT replaced
+    void set(const std::uint8_t* s, std::size_t n) {
+        sa_.resize(n + 1, 0);
+        saca(s, n, sa_);
+        drop_index();
+    }
+    void fit() { sa_.shrink_to_fit(); }                 // src/sa.rs:36-38
+    std::size_t len() const { return n_; }              // src/sa.rs:41-43
+    bool is_empty() const { return n_ == 0; }           // src/sa.rs:46-48
+    std::pair<const std::uint8_t*, std::vector<std::uint32_t>> into_parts() && {  // src/sa.rs:51-53
+        drop_index();
+        return {s_, std::move(sa_)};
+    }
+    // src/sa.rs:57-64
+    static std::optional<SuffixArray> from_parts(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t> sa) {
+        const std::int32_t rc = sab200_check(s, n, sa.data(), sa.size());
+        if (rc < 0) check(rc, "sab200_check");
+        if (rc != 1) return std::nullopt;
+        return SuffixArray(s, n, std::move(sa));
+    }
+    // src/sa.rs:68-70
+    static SuffixArray unchecked_from_parts(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t> sa) {
+        return SuffixArray(s, n, std::move(sa));
+    }
+    // src/sa.rs:89-119
+    void enable_buckets() {
+        if (has_bkt_) return;
+        bkt_.assign(SAB200_BKT_LEN, 0);
+        check(sab200_enable_buckets(s_, n_, bkt_.data()), "sab200_enable_buckets");
+        has_bkt_ = true;
+        drop_index();
+    }
+    void use_gpus(int ngpus) {
+        if (ngpus != ngpus_) {
+            drop_index();
+            ngpus_ = ngpus;
+        }
+    }
+
+    // ---- batched queries: pattern q is pats[offs[q] .. offs[q+1])
+    void search_all_batch(const std::uint8_t* pats, const std::uint64_t* offs, std::size_t np, std::uint32_t* lo,
+                          std::uint32_t* hi) {
+        check(sab200_search_all_batch(index(), pats, offs, np, lo, hi), "sab200_search_all_batch");
+    }
+    void contains_batch(const std::uint8_t* pats, const std::uint64_t* offs, std::size_t np, std::uint8_t* out) {
+        check(sab200_contains_batch(index(), pats, offs, np, out), "sab200_contains_batch");
+    }
+    void search_lcp_batch(const std::uint8_t* pats, const std::uint64_t* offs, std::size_t np, std::uint32_t* start,
+                          std::uint32_t* end) {
+        check(sab200_search_lcp_batch(index(), pats, offs, np, start, end), "sab200_search_lcp_batch");
+    }
+
+    // ---- per-pattern queries (src/sa.rs:164-253)
+    bool contains(const std::uint8_t* pat, std::size_t m) {
+        const std::uint64_t offs[2] = {0, m};
+        std::uint8_t out = 0;
+        contains_batch(pat, offs, 1, &out);
+        return out != 0;
+    }
+    Slice search_all(const std::uint8_t* pat, std::size_t m) {
+        const std::uint64_t offs[2] = {0, m};
+        std::uint32_t lo = 0, hi = 0;
+        search_all_batch(pat, offs, 1, &lo, &hi);
+        return Slice{sa_.data() + lo, (std::size_t)(hi - lo)};
+    }
+    Range search_lcp(const std::uint8_t* pat, std::size_t m) {
+        const std::uint64_t offs[2] = {0, m};
+        std::uint32_t st = 0, en = 0;
+        search_lcp_batch(pat, offs, 1, &st, &en);
+        return Range{st, en};
+    }
+
+    const std::vector<std::uint32_t>& sa() const { return sa_; }   // From<SuffixArray> for Vec<u32>, src/sa.rs:364-368
+    const std::uint8_t* as_ref() const { return s_; }              // AsRef<[u8]>, src/sa.rs:370-374
+    const std::vector<std::uint32_t>* buckets() const { return has_bkt_ ? &bkt_ : nullptr; }
+
+  private:
+    SuffixArray(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t> sa) : s_(s), n_(n), sa_(std::move(sa)) {}
+    sab200_index* index() {
+        if (!ix_) {
+            ix_ = sab200_index_create(s_, n_, sa_.data(), has_bkt_ ? bkt_.data() : nullptr, ngpus_);
+            if (!ix_) throw std::runtime_error(std::string("sab200_index_create: ") + sab200_last_error());
+        }
+        return ix_;
+    }
+    void drop_index() {
+        if (ix_) sab200_index_destroy(ix_);
+        ix_ = nullptr;
+    }
+    const std::uint8_t* s_;
+    std::size_t n_;
+    std::vector<std::uint32_t> sa_;
+    std::vector<std::uint32_t> bkt_;
+    bool has_bkt_ = false;
+    sab200_index* ix_ = nullptr;
+    int ngpus_ = 1;
+};
+
+}  // namespace sab200

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsab200.so")
+# SAB200_LIB: developer override to A/B-test a variant build of the same CUDA engine
+LIB_PATH = os.environ.get("SAB200_LIB") or os.path.join(_HERE, "libsab200.so")
 MAX_LENGTH = 0xFFFFFFFE  # include/sab200.h SAB200_MAX_LENGTH (replaces src/saca.rs:6)
 BKT_LEN = 256 * 257 + 1
 MAX_ROUNDS = 64

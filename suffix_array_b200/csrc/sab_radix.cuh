@@ -14,6 +14,9 @@
 #define SAB_RADIX_BITS 8
 #define SAB_RADIX_BINS 256
 #define SAB_MAX_PASSES 8
+#ifndef SAB_ONESWEEP_MIN_BLOCKS
+#define SAB_ONESWEEP_MIN_BLOCKS 3
+#endif
 
 // look-back word: [63:36] epoch (28 bits) | [35:34] flag | [33:0] count
 #define SAB_LB_VALUE_MASK ((1ull << 34) - 1ull)
@@ -100,6 +103,26 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
     }
 }
 
+// Lanes of the warp holding the same 8-bit digit.  Eight ballots beat the hardware MATCH.ANY
+// instruction here: profiling showed ~45 % of the pass stalled on MATCH results (profiles/).
+#ifndef SAB_MATCH_HW
+#define SAB_MATCH_HW 0
+#endif
+__device__ __forceinline__ u32 match_digit(u32 d) {
+#if SAB_MATCH_HW
+    return __match_any_sync(SAB_FULL, d);
+#else
+    u32 peers = SAB_FULL;
+#pragma unroll
+    for (int bit = 0; bit < SAB_RADIX_BITS; ++bit) {
+        const bool p = (d >> bit) & 1u;
+        const u32 m = __ballot_sync(SAB_FULL, p);
+        peers &= p ? m : ~m;
+    }
+    return peers;
+#endif
+}
+
 // ------------------------------------------------------------------ one onesweep pass
 template <typename KeyT, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
 struct OnesweepCfg {
@@ -113,7 +136,7 @@ struct OnesweepCfg {
 
 // vals_in may be null when IOTA_VAL (payload = position of the record in the input).
 template <typename KeyT, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, SAB_ONESWEEP_MIN_BLOCKS)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
                 u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ gbase,
                 u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch) {
@@ -162,16 +185,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 d = KeyTraits<KeyT>::digit(keys[k], shift);
-        const u32 peers = __match_any_sync(SAB_FULL, d);
+        const u32 peers = match_digit(d);
         const u32 leader = (u32)(__ffs((int)peers) - 1);
+        // The leader's shared-memory atomic returns the running count of this digit in the warp.
+        // Atomics of one warp on one address retire in program order, so item k+1 sees item k's
+        // update; the iterations carry no other dependency and overlap in flight.
         u32 old = 0;
-        if (lane == leader) {
-            old = wh[d];
-            wh[d] = old + (u32)__popc(peers);
-        }
+        if (lane == leader) old = atomicAdd(&wh[d], (u32)__popc(peers));
         old = __shfl_sync(SAB_FULL, old, (int)leader);
         ranks[k] = old + (u32)__popc(peers & lanemask_lt());
-        __syncwarp();
     }
     __syncthreads();
 

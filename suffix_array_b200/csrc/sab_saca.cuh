@@ -1,13 +1,17 @@
 // sab_saca.cuh -- suffix-array construction by GPU prefix doubling.  Replaces the body of
 // saca() (/root/reference/src/saca.rs:9-15), i.e. `sa[0] = n; divsufsort(s, sa[1..])`.
 //
-//   1. alphabet_hist        256-bin byte histogram -> sigma, code LUT (codes 1..sigma; 0 = past the end)
+//   1. alphabet_hist        256-bin byte histogram -> sigma, code LUT (codes 1..sigma; 0 = past the end),
+//                           collision entropy H2 -> how many symbols the initial key needs
 //   2. pack_keys            key[i] = first k codes of suffix i, MSB first, b = ceil(log2(sigma+1)) bits
-//                           each, k = floor(64/b).  Code 0 past the end makes a proper prefix sort first
-//                           and keeps real 0x00 bytes distinct from padding.
+//                           each.  Code 0 past the end makes a proper prefix sort first and keeps real
+//                           0x00 bytes distinct from padding.  k is the smallest count
+//                           with k*H2 >= log2(n) + 6 bits, rounded up to whole radix passes (<= 64 bits).
 //   3. radix sort (key, i)  sab_sort.cuh
-//   4. init_ranks           head flags -> rank[i] = SA position of the first suffix of i's group;
-//                           sa[pos] = i; groups of size > 1 are compacted into the active list
+//   4. init_ranks           head flags -> rank = SA position of the first suffix of the group;
+//                           sa[pos] = i; groups of size > 1 are compacted into the active list and
+//                           only THEIR ranks are scattered; a bucket directory over the sorted keys is
+//                           built on the fly (lazy inverse suffix array, see 4b)
 //   5. rounds, h = k, 2k, 4k, ...   gather r2 = rank[i+h]; sort active by (r1, r2); re-rank with a
 //                           chained scan; settled (singleton) suffixes are written to sa[] and dropped.
 //
@@ -15,12 +19,15 @@
 // symbols agree; rank = SA position of the group head, so a singleton's rank is its final position;
 // rank[n] = 0 (empty suffix); every active i has i + h <= n.
 #pragma once
+#include <math.h>
+
 #include "sab_context.cuh"
 #include "sab_sort.cuh"
 
 #define SAB_SCAN_THREADS 256
 #define SAB_SCAN_ITEMS 8
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
+#define SAB_RANK_EMPTY 0xffffffffu
 
 // ------------------------------------------------------------------ 1. alphabet
 __global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ hist) {
@@ -56,6 +63,17 @@ __global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict
 #define SAB_PACK_ITEMS 8
 #define SAB_PACK_TILE (SAB_PACK_THREADS * SAB_PACK_ITEMS)
 
+// key of the suffix starting at i: k codes, MSB first, code 0 beyond the end of the text
+__device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, int b, int k,
+                                           u64 i) {
+    u64 key = 0;
+    for (int t = 0; t < k; ++t) {
+        const u64 p = i + (u64)t;
+        key = (key << b) | (u64)(p < n ? lut[text[p]] : (u16)0);
+    }
+    return key;
+}
+
 // lut[c] = code of byte c (1..sigma).  key bits [0, k*b) are used.
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
 pack_keys_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, int b, int k, u64* __restrict__ keys) {
@@ -82,7 +100,7 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut
 }
 
 // ------------------------------------------------------------------ block-wide exclusive scan of a POD
-template <typename T, typename Op>
+template <typename T>
 __device__ __forceinline__ T shfl_up_pod(T v, int d) {
     constexpr int W = sizeof(T) / 4;
     union {
@@ -104,7 +122,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& tot
     T incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        T o = shfl_up_pod<T, Op>(incl, d);
+        T o = shfl_up_pod<T>(incl, d);
         if ((int)lane >= d) incl = op(o, incl);
     }
     if (lane == 31) s_wagg[w] = incl;
@@ -117,11 +135,33 @@ __device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& tot
         if (i < (int)w) wprefix = op(wprefix, a);
         tot = op(tot, a);
     }
-    T excl = shfl_up_pod<T, Op>(incl, 1);
+    T excl = shfl_up_pod<T>(incl, 1);
     if (lane == 0) excl = identity;
     total = tot;
     __syncthreads();  // s_wagg reusable
     return op(wprefix, excl);
+}
+
+// ------------------------------------------------------------------ tile I/O: coalesced global <-> blocked registers
+// Global memory is always touched with consecutive lanes on consecutive elements (full sectors); the
+// exchange to the blocked arrangement the scans need (thread t owns elements t*ITEMS .. +ITEMS-1) goes
+// through shared memory, padded by one word per 32 so both access patterns are bank-conflict free.
+#define SAB_PAD(o) ((o) + ((o) >> 5))
+#define SAB_TILE_WORDS (SAB_SCAN_TILE + SAB_SCAN_TILE / 32 + 8)
+
+// striped registers: element k of thread t is tile element t + k*THREADS
+__device__ __forceinline__ void tile_striped_to_blocked(u32 (&v)[SAB_SCAN_ITEMS], u32* __restrict__ s) {
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) s[SAB_PAD(threadIdx.x + k * SAB_SCAN_THREADS)] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) v[k] = s[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)];
+    __syncthreads();
+}
+
+// writes `count` compacted words staged at s[SAB_PAD(0..count)] to g[out_base ..] with coalesced stores
+__device__ __forceinline__ void tile_flush_compact(u32* __restrict__ g, u64 out_base, u32 count, const u32* __restrict__ s) {
+    for (u32 o = threadIdx.x; o < count; o += SAB_SCAN_THREADS) g[out_base + o] = s[SAB_PAD(o)];
 }
 
 // ------------------------------------------------------------------ 4. ranks after the initial sort
@@ -138,28 +178,47 @@ struct RankScanOp {
     }
 };
 
-// K, I: records sorted by key.  Writes rank[I[j]] = 1 + (index of the head of j's group),
-// sa[j+1] = I[j], sa[0] = n, and compacts records of groups larger than one into (act_r1, act_idx).
+// K, I: records sorted by key.  The rank of record j is r = 1 + (index of the head of j's group).
+//   sa[j+1] = I[j], sa[0] = n                         (coalesced copy)
+//   records of groups larger than one -> (act_r1, act_idx), and rank[I[j]] = r for them only
+//   dir[key >> dir_shift] = j at the first record of every directory bucket (lazy ISA, see 4b)
 __global__ void __launch_bounds__(SAB_SCAN_THREADS)
 init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32* __restrict__ rank,
                   u32* __restrict__ sa, u32* __restrict__ act_r1, u32* __restrict__ act_idx, u32* __restrict__ d_count,
-                  TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
+                  u32* __restrict__ dir, int dir_shift, TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
     SAB_SHARED_VAR(u32, s_tile);
+    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
+    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 j0 = (u64)tile * SAB_SCAN_TILE + (u64)threadIdx.x * SAB_SCAN_ITEMS;
-    u64 key[SAB_SCAN_ITEMS + 2];  // key[0] = predecessor, key[ITEMS+1] = successor
-    u32 idx[SAB_SCAN_ITEMS];
-    const u64 SENT = ~0ull;  // never compared: guarded by index tests below
-    key[0] = (j0 > 0 && j0 - 1 < n) ? K[j0 - 1] : SENT;
+    const u64 base = (u64)tile * SAB_SCAN_TILE;
+    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+
+    // ---- coalesced loads (striped), sa copy on the way, then exchange to blocked
+    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        key[k + 1] = j < n ? K[j] : SENT;
-        idx[k] = j < n ? I[j] : 0u;
+        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
+        u64 key = 0;
+        u32 ix = 0;
+        if (j < n) {
+            key = K[j];
+            ix = I[j];
+            sa[j + 1] = ix;
+        }
+        klo[k] = (u32)key;
+        khi[k] = (u32)(key >> 32);
+        idx[k] = ix;
     }
-    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < n) ? K[j0 + SAB_SCAN_ITEMS] : SENT;
+    tile_striped_to_blocked(klo, s_a);
+    tile_striped_to_blocked(khi, s_b);
+    tile_striped_to_blocked(idx, s_a);
+    u64 key[SAB_SCAN_ITEMS + 2];  // key[0] = predecessor, key[ITEMS+1] = successor
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
+    key[0] = (j0 > 0 && j0 - 1 < n) ? K[j0 - 1] : 0ull;
+    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < n) ? K[j0 + SAB_SCAN_ITEMS] : 0ull;
 
     RankScan mine;
     mine.head = 0;
@@ -174,6 +233,7 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
             if (head) {
                 headbits |= 1u << k;
                 mine.head = (u32)j;
+                if (dir && (j == 0 || (key[k + 1] >> dir_shift) != (key[k] >> dir_shift))) dir[key[k + 1] >> dir_shift] = (u32)j;
             }
             if (!(head && next_head)) {
                 activebits |= 1u << k;
@@ -187,41 +247,105 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
     RankScan total;
     RankScan excl = block_exclusive_scan<RankScan, RankScanOp, SAB_SCAN_THREADS>(mine, RankScanOp(), ident, total);
     RankScan prefix = tile_exclusive_prefix<RankScan, RankScanOp>(st, tile, total, RankScanOp(), ident);
-    RankScan run = RankScanOp()(prefix, excl);
-    if (tile == 0 && threadIdx.x == 0) sa[0] = (u32)n;
+    u32 head_run = prefix.head > excl.head ? prefix.head : excl.head;
+    u32 local = excl.cnt;  // position of this thread's first active record inside the tile's compacted output
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
         const u64 j = j0 + k;
         if (j < n) {
-            if (headbits & (1u << k)) run.head = (u32)j;
-            const u32 r = run.head + 1u;
-            rank[idx[k]] = r;
-            sa[j + 1] = idx[k];
+            if (headbits & (1u << k)) head_run = (u32)j;
             if (activebits & (1u << k)) {
-                act_r1[run.cnt] = r;
-                act_idx[run.cnt] = idx[k];
-                run.cnt++;
+                const u32 r = head_run + 1u;
+                rank[idx[k]] = r;
+                s_a[SAB_PAD(local)] = r;
+                s_b[SAB_PAD(local)] = idx[k];
+                ++local;
             }
         }
     }
-    const u64 last = n - 1;
-    if (last >= j0 && last < j0 + SAB_SCAN_ITEMS) *d_count = run.cnt;
-    if (tile == 0 && threadIdx.x == 0) rank[n] = 0u;
+    __syncthreads();
+    tile_flush_compact(act_r1, prefix.cnt, total.cnt, s_a);
+    tile_flush_compact(act_idx, prefix.cnt, total.cnt, s_b);
+    if (threadIdx.x == 0) {
+        if (base + SAB_SCAN_TILE >= n) *d_count = prefix.cnt + total.cnt;  // last tile
+        if (tile == 0) {
+            sa[0] = (u32)n;
+            rank[n] = 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 4b. lazy inverse suffix array
+// Scattering all n initial ranks costs a partial-sector write per suffix (~30 G/s on B200, 35-50 ms per
+// GiB) although only i + h of the few active i are ever looked up.  So rank[] starts EMPTY except for
+// active suffixes; a lookup that hits EMPTY is a suffix that was unique after the initial sort, and
+// its rank is 1 + its position in the (kept) sorted key array: re-pack its key from the text, jump
+// through the bucket directory, gallop + bisect.  Texts where most suffixes stay active fall back
+// to filling rank[] completely (fill_settled_ranks_kernel) so the sorted keys can be dropped.
+struct LazyIsa {
+    const u8* text;
+    const u16* lut;
+    const u64* sorted_keys;  // null -> rank[] is complete
+    const u32* dir;
+    u64 n;
+    int b, k, dir_shift;
+};
+
+__device__ __forceinline__ u32 lazy_rank_lookup(const LazyIsa& z, u64 t) {
+    const u64 key = pack_key_at(z.text, z.n, z.lut, z.b, z.k, t);
+    u64 lo = z.dir[key >> z.dir_shift];
+    u64 hi = lo, step = 1;
+    while (hi < z.n && z.sorted_keys[hi] < key) {  // gallop: keys[lo-1] < key stays true
+        lo = hi + 1;
+        hi += step;
+        step <<= 1;
+    }
+    if (hi > z.n) hi = z.n;
+    while (lo < hi) {  // first position whose key is >= key; the key of t is present exactly once
+        const u64 mid = lo + (hi - lo) / 2;
+        if (z.sorted_keys[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (u32)lo + 1u;
+}
+
+// rank[I[j]] = j + 1 for every singleton record (complete-ISA fallback)
+__global__ void __launch_bounds__(256)
+fill_settled_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32* __restrict__ rank) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u64 key = K[j];
+    const bool head = (j == 0) || K[j - 1] != key;
+    const bool next_head = (j + 1 >= n) || K[j + 1] != key;
+    if (head && next_head) rank[I[j]] = (u32)j + 1u;
 }
 
 // ------------------------------------------------------------------ 5a. gather the second rank
 #define SAB_GATHER_THREADS 256
 #define SAB_GATHER_ITEMS 4
 
+__device__ __forceinline__ u32 rank_at(u32* __restrict__ rank, const LazyIsa& z, u64 t) {
+    u32 r = rank[t];
+    if (r == SAB_RANK_EMPTY) {  // only possible while z.sorted_keys != null
+        r = lazy_rank_lookup(z, t);
+        rank[t] = r;  // memoise; racing writers store the same value
+    }
+    return r;
+}
+
 // key64[j] = (r1[j] << 32) | rank[idx[j] + h]
 __global__ void __launch_bounds__(SAB_GATHER_THREADS)
-gather_rank2_kernel(const u32* __restrict__ act_r1, const u32* __restrict__ act_idx, u64 m, u64 h,
-                    const u32* __restrict__ rank, u64* __restrict__ key64) {
+gather_rank2_kernel(const u32* __restrict__ act_r1, const u32* __restrict__ act_idx, u64 m, u64 h, u32* __restrict__ rank,
+                    LazyIsa z, u64* __restrict__ key64) {
     const u64 j0 = ((u64)blockIdx.x * SAB_GATHER_THREADS + threadIdx.x) * SAB_GATHER_ITEMS;
     if (j0 + SAB_GATHER_ITEMS <= m) {
         const uint4 r1 = *(const uint4*)(act_r1 + j0);
         const uint4 ix = *(const uint4*)(act_idx + j0);
-        const u32 a = rank[(u64)ix.x + h], b = rank[(u64)ix.y + h], c = rank[(u64)ix.z + h], d = rank[(u64)ix.w + h];
+        u32 a = rank[(u64)ix.x + h], b = rank[(u64)ix.y + h], c = rank[(u64)ix.z + h], d = rank[(u64)ix.w + h];
+        if (a == SAB_RANK_EMPTY) a = rank_at(rank, z, (u64)ix.x + h);
+        if (b == SAB_RANK_EMPTY) b = rank_at(rank, z, (u64)ix.y + h);
+        if (c == SAB_RANK_EMPTY) c = rank_at(rank, z, (u64)ix.z + h);
+        if (d == SAB_RANK_EMPTY) d = rank_at(rank, z, (u64)ix.w + h);
         ulonglong2 o0, o1;
         o0.x = ((u64)r1.x << 32) | a;
         o0.y = ((u64)r1.y << 32) | b;
@@ -230,7 +354,7 @@ gather_rank2_kernel(const u32* __restrict__ act_r1, const u32* __restrict__ act_
         *(ulonglong2*)(key64 + j0) = o0;
         *(ulonglong2*)(key64 + j0 + 2) = o1;
     } else {
-        for (u64 j = j0; j < m; ++j) key64[j] = ((u64)act_r1[j] << 32) | rank[(u64)act_idx[j] + h];
+        for (u64 j = j0; j < m; ++j) key64[j] = ((u64)act_r1[j] << 32) | rank_at(rank, z, (u64)act_idx[j] + h);
     }
 }
 
@@ -260,19 +384,35 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
               u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ d_count, TileState<RerankScan> st,
               u32* __restrict__ ticket, u32 ticket_base) {
     SAB_SHARED_VAR(u32, s_tile);
+    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
+    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
     __syncthreads();
     const u32 tile = s_tile;
-    const u64 j0 = (u64)tile * SAB_SCAN_TILE + (u64)threadIdx.x * SAB_SCAN_ITEMS;
-    u64 key[SAB_SCAN_ITEMS + 2];
-    u32 idx[SAB_SCAN_ITEMS];
-    key[0] = (j0 > 0 && j0 - 1 < m) ? S[j0 - 1] : 0ull;
+    const u64 base = (u64)tile * SAB_SCAN_TILE;
+    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+
+    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        key[k + 1] = j < m ? S[j] : 0ull;
-        idx[k] = j < m ? I[j] : 0u;
+        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
+        u64 key = 0;
+        u32 ix = 0;
+        if (j < m) {
+            key = S[j];
+            ix = I[j];
+        }
+        klo[k] = (u32)key;
+        khi[k] = (u32)(key >> 32);
+        idx[k] = ix;
     }
+    tile_striped_to_blocked(klo, s_a);
+    tile_striped_to_blocked(khi, s_b);
+    tile_striped_to_blocked(idx, s_a);
+    u64 key[SAB_SCAN_ITEMS + 2];
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
+    key[0] = (j0 > 0 && j0 - 1 < m) ? S[j0 - 1] : 0ull;
     key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < m) ? S[j0 + SAB_SCAN_ITEMS] : 0ull;
 
     RerankScan mine;
@@ -309,6 +449,7 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
     RerankScan excl = block_exclusive_scan<RerankScan, RerankScanOp, SAB_SCAN_THREADS>(mine, RerankScanOp(), ident, total);
     RerankScan prefix = tile_exclusive_prefix<RerankScan, RerankScanOp>(st, tile, total, RerankScanOp(), ident);
     RerankScan run = RerankScanOp()(prefix, excl);
+    u32 local = excl.cnt;
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
         const u64 j = j0 + k;
@@ -319,16 +460,18 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
             const u32 nr = r1 + (run.nhs - run.ogs);
             if (nr != r1) rank[idx[k]] = nr;
             if (keepbits & (1u << k)) {
-                out_r1[run.cnt] = nr;
-                out_idx[run.cnt] = idx[k];
-                run.cnt++;
+                s_a[SAB_PAD(local)] = nr;
+                s_b[SAB_PAD(local)] = idx[k];
+                ++local;
             } else {
                 sa[nr] = idx[k];
             }
         }
     }
-    const u64 last = m - 1;
-    if (last >= j0 && last < j0 + SAB_SCAN_ITEMS) *d_count = run.cnt;
+    __syncthreads();
+    tile_flush_compact(out_r1, prefix.cnt, total.cnt, s_a);
+    tile_flush_compact(out_idx, prefix.cnt, total.cnt, s_b);
+    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= m) *d_count = prefix.cnt + total.cnt;
 }
 
 // ------------------------------------------------------------------ driver (device pointers)
@@ -341,8 +484,18 @@ static inline int sab_ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
-    return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) + 4096;
+    int dir_bits = sab_ceil_log2_u64(n) - 4;
+    if (dir_bits > 26) dir_bits = 26;
+    if (dir_bits < 1) dir_bits = 1;
+    return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) +
+           sab_align_up((((size_t)1 << dir_bits) + 8) * 4, 256) + 4096;
 }
+
+#ifdef SAB_EMU
+#define SAB_MARGIN_BITS 2.0  // emulator runs are tiny: keep the doubling rounds exercised
+#else
+#define SAB_MARGIN_BITS 6.0
+#endif
 
 // d_text: n bytes; d_sa: n+1 u32; both device memory.  Work is enqueued on c->stream and the
 // stream is synchronised before returning.
@@ -386,13 +539,30 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     memcpy(h_hist, c->h_small + 64, sizeof(h_hist));
     u16 lut[256];
     u32 sigma = 0;
+    double sum_p2 = 0.0;
     for (int ch = 0; ch < 256; ++ch) {
         if (h_hist[ch]) ++sigma;
         lut[ch] = (u16)(h_hist[ch] ? sigma : 0);
+        const double p = (double)h_hist[ch] / (double)n;
+        sum_p2 += p * p;
     }
     int b = sab_ceil_log2_u64((u64)sigma + 1);  // codes 0..sigma
     if (b < 1) b = 1;
-    const int k = 64 / b;
+    // symbols per key: enough collision entropy to separate n random suffixes with SAB_MARGIN_BITS to
+    // spare, rounded up to whole 8-bit radix passes; never more than fit in 64 bits
+    const int k_full = 64 / b;
+    int k = k_full;
+    const double h2 = sum_p2 < 1.0 ? -log2(sum_p2) : 0.0;
+    if (h2 > 1e-3) {
+        const double want = (log2((double)n) + SAB_MARGIN_BITS) / h2;
+        if (want < (double)k_full) {
+            int kmin = (int)ceil(want);
+            if (kmin < 1) kmin = 1;
+            const int passes = (kmin * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
+            k = passes * SAB_RADIX_BITS / b;
+            if (k > k_full) k = k_full;
+        }
+    }
     S.sigma = sigma;
     S.bits_per_symbol = (u32)b;
     S.symbols_per_key = (u32)k;
@@ -408,27 +578,73 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     S.kernel_launches++;
 
     // 3. sort (key, i)
-    SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, k * b, /*iota=*/true, &S.passes[0]));
+    const int key_bits = k * b;
+    SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, key_bits, /*iota=*/true, &S.passes[0]));
 
-    // 4. ranks, SA skeleton, active list
+    // 4. ranks, SA skeleton, active list, bucket directory over the sorted keys
     u32* d_m = c->d_counters;
+    const u64* sortedK = buf.k[buf.cur];
+    const u32* sortedI = buf.v[buf.cur];
+    u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
+    int dir_bits = sab_ceil_log2_u64(n) - 4;
+    if (dir_bits > 26) dir_bits = 26;
+    if (dir_bits > key_bits) dir_bits = key_bits;
+    if (dir_bits < 1) dir_bits = 1;
+    const int dir_shift = key_bits - dir_bits;
+    u32* dir = sab_arena_take<u32>(c, ((size_t)1 << dir_bits) + 8);
+    SAB_CUDA_TRY(cudaMemsetAsync(rank, 0xff, (n + 1) * sizeof(u32), st));
     {
         const u64 tiles = div_up64(n, SAB_SCAN_TILE);
         TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
         sab_prof_begin(c, 3);
-        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)buf.k[buf.cur],
-                   (const u32*)buf.v[buf.cur], n, rank, d_sa, r1buf, act_idx, d_m, ts, c->d_ticket, c->ticket_host);
+        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, n, rank, d_sa, r1buf,
+                   act_idx, d_m, dir, dir_shift, ts, c->d_ticket, c->ticket_host);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         c->ticket_host += (u32)tiles;
         S.kernel_launches++;
     }
-    buf.cur ^= 1;  // v[cur] now holds act_idx; k[cur] is free for the composite keys
     SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
     u64 m = c->h_small[0];
     S.active[0] = m;
+    if (m == 0) {
+        S.rounds = 0;
+        return SAB_OK;
+    }
+
+    // 4b. lazy or complete inverse suffix array
+    LazyIsa z;
+    z.text = d_text;
+    z.lut = d_lut;
+    z.dir = dir;
+    z.n = n;
+    z.b = b;
+    z.k = k;
+    z.dir_shift = dir_shift;
+    SortBuffers<u64> rb;  // buffers of the rounds
+    if (m <= n / 4) {
+        // keep the sorted keys; the composite keys of the rounds ping-pong inside the other key buffer
+        z.sorted_keys = sortedK;
+        rb.k[0] = free_keys;
+        rb.k[1] = free_keys + sab_align_up((size_t)(n + 8) / 2, 32);
+        rb.v[0] = act_idx;
+        rb.v[1] = buf.v[buf.cur];
+        rb.cur = 0;
+    } else {
+        z.sorted_keys = nullptr;
+        sab_prof_begin(c, 3);
+        SAB_LAUNCH(fill_settled_ranks_kernel, (unsigned)div_up64(n, 256), 256, 0, st, sortedK, sortedI, n, rank);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
+        rb.k[0] = buf.k[buf.cur ^ 1];
+        rb.k[1] = buf.k[buf.cur];
+        rb.v[0] = act_idx;
+        rb.v[1] = buf.v[buf.cur];
+        rb.cur = 0;
+    }
 
     // 5. doubling rounds
     u64 h = (u64)k;
@@ -443,24 +659,24 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
         }
         sab_prof_begin(c, 4);
         SAB_LAUNCH(gather_rank2_kernel, (unsigned)div_up64(m, (u64)SAB_GATHER_THREADS * SAB_GATHER_ITEMS), SAB_GATHER_THREADS,
-                   0, st, (const u32*)r1buf, (const u32*)buf.v[buf.cur], m, h, (const u32*)rank, buf.k[buf.cur]);
+                   0, st, (const u32*)r1buf, (const u32*)rb.v[rb.cur], m, h, rank, z, rb.k[rb.cur]);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         S.kernel_launches++;
-        SAB_TRY(sab_radix_sort<u64>(c, buf, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+        SAB_TRY(sab_radix_sort<u64>(c, rb, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
         {
             const u64 tiles = div_up64(m, SAB_SCAN_TILE);
             TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
             sab_prof_begin(c, 3);
-            SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)buf.k[buf.cur],
-                       (const u32*)buf.v[buf.cur], m, rank, d_sa, r1buf, buf.v[buf.cur ^ 1], d_m, ts, c->d_ticket,
+            SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)rb.k[rb.cur],
+                       (const u32*)rb.v[rb.cur], m, rank, d_sa, r1buf, rb.v[rb.cur ^ 1], d_m, ts, c->d_ticket,
                        c->ticket_host);
             sab_prof_end(c);
             SAB_LAUNCH_CHECK();
             c->ticket_host += (u32)tiles;
             S.kernel_launches++;
         }
-        buf.cur ^= 1;
+        rb.cur ^= 1;
         SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
         SAB_CUDA_TRY(cudaStreamSynchronize(st));
         m = c->h_small[0];

@@ -13,13 +13,19 @@ struct SortBuffers {
 // tile shape of the pass kernel (see DESIGN.md "onesweep tile")
 template <typename KeyT>
 struct PassShape;
+#ifndef SAB_PASS_THREADS
+#define SAB_PASS_THREADS 256
+#endif
+#ifndef SAB_PASS_ITEMS
+#define SAB_PASS_ITEMS 16
+#endif
 template <>
 struct PassShape<u64> {
-    static constexpr int THREADS = 256, ITEMS = 16;
+    static constexpr int THREADS = SAB_PASS_THREADS, ITEMS = SAB_PASS_ITEMS;
 };
 template <>
 struct PassShape<u32> {
-    static constexpr int THREADS = 256, ITEMS = 16;
+    static constexpr int THREADS = SAB_PASS_THREADS, ITEMS = SAB_PASS_ITEMS;
 };
 
 template <typename KeyT, bool IOTA>
