@@ -108,6 +108,11 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
 #ifndef SAB_MATCH_HW
 #define SAB_MATCH_HW 0
 #endif
+// every SAB_HW_MATCH_EVERY-th item of a thread uses the MATCH unit instead (0 = never): lets the
+// otherwise idle MATCH pipe take part of the ranking work off the issue slots
+#ifndef SAB_HW_MATCH_EVERY
+#define SAB_HW_MATCH_EVERY 0
+#endif
 __device__ __forceinline__ u32 match_digit(u32 d) {
 #if SAB_MATCH_HW
     return __match_any_sync(SAB_FULL, d);
@@ -131,14 +136,39 @@ struct OnesweepCfg {
     static constexpr size_t KEY_BYTES = (size_t)TILE * sizeof(KeyT);
     static constexpr size_t VAL_BYTES = HAS_VAL ? (size_t)TILE * sizeof(u32) : 0;
     static constexpr size_t WHIST_BYTES = (size_t)WARPS * SAB_RADIX_BINS * sizeof(u32);
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * (sizeof(u32) + sizeof(u64));
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * 2 * sizeof(u32);
+};
+
+// Digit extractors.  The padding key of a partial tile (all ones) must map to the last bin in use.
+template <typename KeyT>
+struct ShiftDigit {  // radix digit: bits [shift, shift+8)
+    int shift;
+    __device__ __forceinline__ u32 operator()(KeyT k) const { return (u32)(k >> shift) & 0xffu; }
+};
+#define SAB_MAX_RANKS 16
+struct SplitterDigit {  // destination rank of a key: number of splitters <= key (multi-GPU sample sort)
+    u64 s[SAB_MAX_RANKS - 1];
+    int np;
+    __device__ __forceinline__ u32 operator()(u64 k) const {
+        u32 d = 0;
+#pragma unroll
+        for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) d += (i < np && s[i] <= k) ? 1u : 0u;
+        return d;
+    }
+};
+struct OwnerDigit {  // owner rank of text position key + add under a block distribution of width B
+    u32 add, B, pmax;
+    __device__ __forceinline__ u32 operator()(u32 k) const {
+        const u32 o = (u32)(((u64)k + add) / B);
+        return o < pmax ? o : pmax;
+    }
 };
 
 // vals_in may be null when IOTA_VAL (payload = position of the record in the input).
-template <typename KeyT, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
+template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, SAB_ONESWEEP_MIN_BLOCKS)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
-                u32* __restrict__ vals_out, u64 n, int shift, const u64* __restrict__ gbase,
+                u32* __restrict__ vals_out, u64 n, DigitOp dop, const u64* __restrict__ gbase,
                 u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch) {
     typedef OnesweepCfg<KeyT, HAS_VAL, IOTA_VAL, THREADS, ITEMS> Cfg;
     static_assert(THREADS >= SAB_RADIX_BINS && THREADS % 32 == 0, "one look-back lane per bin");
@@ -146,8 +176,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     SAB_DYN_SMEM(smem);
     KeyT* s_keys = (KeyT*)smem;
     u32* s_vals = (u32*)(smem + Cfg::KEY_BYTES);
-    u64* s_goff = (u64*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES);          // [256] global offset - local start
-    u32* s_whist = (u32*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES + SAB_RADIX_BINS * sizeof(u64));  // [WARPS][256]
+    u32* s_goff = (u32*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES);          // [256] global record index - local start (mod 2^32)
+    u32* s_whist = s_goff + SAB_RADIX_BINS;                                  // [WARPS][256]
     u32* s_binstart = s_whist + WARPS * SAB_RADIX_BINS;                     // [256]
     SAB_SHARED_VAR(u32, s_tile);
     SAB_SHARED_ARRAY(u32, s_wsum, 8);
@@ -160,23 +190,31 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     const u64 tile_base = (u64)tile * TILE;
     const u64 remaining = n - tile_base;
     const u32 valid = remaining < (u64)TILE ? (u32)remaining : (u32)TILE;
+    const bool full = valid == (u32)TILE;  // block-uniform: all tiles but the last take the unguarded paths
 
     // ---- load (warp-striped: item k of lane l is record w*WTILE + k*32 + l of the tile)
     KeyT keys[ITEMS];
     u32 vals[ITEMS];
     u32 ranks[ITEMS];
     const u32 wofs = w * WTILE + lane;
+    const KeyT* kin = keys_in + tile_base + wofs;
+    const u32* vin = IOTA_VAL ? nullptr : vals_in + tile_base + wofs;
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 o = wofs + k * 32;
-        keys[k] = o < valid ? keys_in[tile_base + o] : KeyTraits<KeyT>::max_key();
-    }
-    if (HAS_VAL) {
+        for (int k = 0; k < ITEMS; ++k) keys[k] = kin[k * 32];
+        if (HAS_VAL) {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const u32 o = wofs + k * 32;
-            if (IOTA_VAL) vals[k] = (u32)(tile_base + o);
-            else vals[k] = o < valid ? vals_in[tile_base + o] : 0u;
+            for (int k = 0; k < ITEMS; ++k) vals[k] = IOTA_VAL ? (u32)(tile_base + wofs + k * 32) : vin[k * 32];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) keys[k] = (wofs + k * 32 < valid) ? kin[k * 32] : KeyTraits<KeyT>::max_key();
+        if (HAS_VAL) {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                if (IOTA_VAL) vals[k] = (u32)(tile_base + wofs + k * 32);
+                else vals[k] = (wofs + k * 32 < valid) ? vin[k * 32] : 0u;
+            }
         }
     }
 
@@ -184,8 +222,10 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     u32* wh = s_whist + w * SAB_RADIX_BINS;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const u32 d = KeyTraits<KeyT>::digit(keys[k], shift);
-        const u32 peers = match_digit(d);
+        const u32 d = dop(keys[k]);
+        const u32 peers = (SAB_HW_MATCH_EVERY > 0 && (k % (SAB_HW_MATCH_EVERY > 0 ? SAB_HW_MATCH_EVERY : 1)) == 0)
+                              ? __match_any_sync(SAB_FULL, d)
+                              : match_digit(d);
         const u32 leader = (u32)(__ffs((int)peers) - 1);
         // The leader's shared-memory atomic returns the running count of this digit in the warp.
         // Atomics of one warp on one address retire in program order, so item k+1 sees item k's
@@ -213,6 +253,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         st_relaxed_u64(lb, etag | (tile == 0 ? SAB_LB_FLAG_INCLUSIVE : SAB_LB_FLAG_PARTIAL) | (u64)my_count);
     }
     // ---- block-exclusive scan of the 256 bin counts -> local start of every bin in the tile
+    u32 my_start = 0;
     {
         u32 incl = warp_incl_sum(my_count);
         if (tid < SAB_RADIX_BINS && lane == 31) s_wsum[w] = incl;
@@ -220,7 +261,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         if (tid < SAB_RADIX_BINS) {
             u32 woff = 0;
             for (u32 i = 0; i < w; ++i) woff += s_wsum[i];
-            s_binstart[tid] = woff + incl - my_count;
+            my_start = woff + incl - my_count;
+            s_binstart[tid] = my_start;
         }
     }
     // ---- decoupled look-back, one lane per bin
@@ -241,14 +283,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             }
             st_relaxed_u64(lb, etag | SAB_LB_FLAG_INCLUSIVE | (excl + (u64)my_count));
         }
-        s_goff[tid] = gbase[tid] + excl - (u64)s_binstart[tid];
+        // record indices are < 2^32 (N <= 2^32 - 1): keep the per-bin offset as a wrapping u32
+        s_goff[tid] = (u32)(gbase[tid] + excl) - my_start;
     }
     __syncthreads();
 
     // ---- scatter into shared memory in sorted order
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const u32 d = KeyTraits<KeyT>::digit(keys[k], shift);
+        const u32 d = dop(keys[k]);
         const u32 pos = s_binstart[d] + s_whist[w * SAB_RADIX_BINS + d] + ranks[k];
         s_keys[pos] = keys[k];
         if (HAS_VAL) s_vals[pos] = vals[k];
@@ -256,14 +299,25 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     __syncthreads();
 
     // ---- coalesced write-out: consecutive shared slots of one bin are consecutive in global memory
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 p = tid + k * THREADS;
-        if (p < valid) {
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 p = tid + k * THREADS;
             const KeyT key = s_keys[p];
-            const u64 dst = s_goff[KeyTraits<KeyT>::digit(key, shift)] + p;
+            const u32 dst = s_goff[dop(key)] + p;
             keys_out[dst] = key;
             if (HAS_VAL) vals_out[dst] = s_vals[p];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 p = tid + k * THREADS;
+            if (p < valid) {
+                const KeyT key = s_keys[p];
+                const u32 dst = s_goff[dop(key)] + p;
+                keys_out[dst] = key;
+                if (HAS_VAL) vals_out[dst] = s_vals[p];
+            }
         }
     }
 }

@@ -5,8 +5,8 @@
 //                           collision entropy H2 -> how many symbols the initial key needs
 //   2. pack_keys            key[i] = first k codes of suffix i, MSB first, b = ceil(log2(sigma+1)) bits
 //                           each.  Code 0 past the end makes a proper prefix sort first and keeps real
-//                           0x00 bytes distinct from padding.  k is the smallest count
-//                           with k*H2 >= log2(n) + 6 bits, rounded up to whole radix passes (<= 64 bits).
+//                           0x00 bytes distinct from padding.  k = whole radix passes chosen by a
+//                           cost model (passes vs expected ties from the collision entropy H2), <= 64 bits.
 //   3. radix sort (key, i)  sab_sort.cuh
 //   4. init_ranks           head flags -> rank = SA position of the first suffix of the group;
 //                           sa[pos] = i; groups of size > 1 are compacted into the active list and
@@ -492,9 +492,9 @@ static inline size_t sab_saca_workspace_bytes(u64 n) {
 }
 
 #ifdef SAB_EMU
-#define SAB_MARGIN_BITS 2.0  // emulator runs are tiny: keep the doubling rounds exercised
+#define SAB_ACTIVE_COST 30.0  // emulator runs are tiny: keep the doubling rounds exercised
 #else
-#define SAB_MARGIN_BITS 6.0
+#define SAB_ACTIVE_COST 300.0
 #endif
 
 // d_text: n bytes; d_sa: n+1 u32; both device memory.  Work is enqueued on c->stream and the
@@ -550,17 +550,27 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     if (b < 1) b = 1;
     // symbols per key: enough collision entropy to separate n random suffixes with SAB_MARGIN_BITS to
     // spare, rounded up to whole 8-bit radix passes; never more than fit in 64 bits
+    // Cost model, in bytes moved per suffix: P radix passes of 24 B each, plus ~SAB_ACTIVE_COST bytes over
+    // all doubling rounds for every suffix still tied after the initial sort; a suffix stays tied with
+    // probability ~ n * 2^-(k*H2) (H2 = order-0 collision entropy; higher-order structure only makes the
+    // estimate optimistic, never the result wrong).
     const int k_full = 64 / b;
     int k = k_full;
     const double h2 = sum_p2 < 1.0 ? -log2(sum_p2) : 0.0;
     if (h2 > 1e-3) {
-        const double want = (log2((double)n) + SAB_MARGIN_BITS) / h2;
-        if (want < (double)k_full) {
-            int kmin = (int)ceil(want);
-            if (kmin < 1) kmin = 1;
-            const int passes = (kmin * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
-            k = passes * SAB_RADIX_BITS / b;
-            if (k > k_full) k = k_full;
+        double best = 1e300;
+        const int p_full = (k_full * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
+        for (int p = 1; p <= p_full; ++p) {
+            int kp = p * SAB_RADIX_BITS / b;
+            if (kp > k_full) kp = k_full;
+            if (kp < 1) continue;
+            double tied = exp2(log2((double)n) - (double)kp * h2);
+            if (tied > 1.0) tied = 1.0;
+            const double cost = 24.0 * p + SAB_ACTIVE_COST * tied;
+            if (cost < best - 1e-9) {
+                best = cost;
+                k = kp;
+            }
         }
     }
     S.sigma = sigma;

@@ -28,9 +28,9 @@ struct PassShape<u32> {
     static constexpr int THREADS = SAB_PASS_THREADS, ITEMS = SAB_PASS_ITEMS;
 };
 
-template <typename KeyT, bool IOTA>
-static int sab_launch_pass(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, int shift,
-                           const u64* gbase) {
+template <typename KeyT, bool IOTA, typename DigitOp>
+static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, DigitOp dop,
+                              const u64* gbase) {
     constexpr int THREADS = PassShape<KeyT>::THREADS, ITEMS = PassShape<KeyT>::ITEMS;
     typedef OnesweepCfg<KeyT, true, IOTA, THREADS, ITEMS> Cfg;
     const u64 tiles = div_up64(n, (u64)Cfg::TILE);
@@ -39,16 +39,12 @@ static int sab_launch_pass(SabContext* c, const KeyT* kin, KeyT* kout, const u32
         c->lb_epoch = 0;
     }
     const u32 epoch = ++c->lb_epoch;
-    auto kern = onesweep_kernel<KeyT, true, IOTA, THREADS, ITEMS>;
+    auto kern = onesweep_kernel<KeyT, DigitOp, true, IOTA, THREADS, ITEMS>;
 #ifndef SAB_EMU
-    static bool attr_set = false;
-    if (!attr_set) {
-        SAB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    SAB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));  // per device
 #endif
     sab_prof_begin(c, 0);
-    SAB_LAUNCH(kern, (unsigned)tiles, THREADS, Cfg::SMEM, c->stream, kin, kout, vin, vout, n, shift, gbase,
+    SAB_LAUNCH(kern, (unsigned)tiles, THREADS, Cfg::SMEM, c->stream, kin, kout, vin, vout, n, dop, gbase,
                c->d_lookback, c->d_ticket, c->ticket_host, epoch);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
@@ -58,6 +54,14 @@ static int sab_launch_pass(SabContext* c, const KeyT* kin, KeyT* kout, const u32
     c->stats.radix_pass_bytes += 2ull * (sizeof(KeyT) + sizeof(u32)) * n;
     c->stats.kernel_launches += 1;
     return SAB_OK;
+}
+
+template <typename KeyT, bool IOTA>
+static int sab_launch_pass(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, int shift,
+                           const u64* gbase) {
+    ShiftDigit<KeyT> dop;
+    dop.shift = shift;
+    return sab_launch_pass_op<KeyT, IOTA, ShiftDigit<KeyT> >(c, kin, kout, vin, vout, n, dop, gbase);
 }
 
 // Sorts the n records (k[cur], v[cur]) by key bits [begin_bit, end_bit), stable, ascending.  When
