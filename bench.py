@@ -29,7 +29,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+C4_BYTES = int(3.9 * (1 << 30))  # 4 187 593 113: the u32 index limit configuration
+
 WORKLOADS = {
+    "c4": ("3.9 GiB mixed text (first half uniform bytes, second half English-like), BASELINE.json configs[3]",
+           C4_BYTES, "mixed"),
     "c2": ("1 GiB DNA-like text (sigma=4, planted repeats), BASELINE.json configs[1]", 1 << 30, "dna_like"),
     "c1": ("64 MiB uniform-random bytes (sigma=256), BASELINE.json configs[0]", 64 << 20, "uniform_bytes"),
     "c3": ("256 MiB repetitive text (1 MiB block, 1e-4 mutations), BASELINE.json configs[2]", 256 << 20, "repetitive"),
@@ -40,7 +44,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if 
 def make_text(workload, n, seed_shift=0):
     from suffix_array_b200 import gen
     fn = getattr(gen, WORKLOADS[workload][2])
-    seed = {"c1": gen.SEED_C1, "c2": gen.SEED_C2, "c3": gen.SEED_C3}[workload] + seed_shift
+    seed = {"c1": gen.SEED_C1, "c2": gen.SEED_C2, "c3": gen.SEED_C3, "c4": gen.SEED_C4}[workload] + seed_shift
     return fn(n, seed)
 
 
@@ -136,7 +140,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c2 on one GPU (BASELINE.json configs[1]), c4 on several (configs[3])")
     ap.add_argument("--n-mib", type=int, default=0, help="override the text size (MiB); 0 = the named config")
     ap.add_argument("--ref-sample-mib", type=int, default=16)
     ap.add_argument("--cpu-sample-mib", type=int, default=32)
@@ -146,6 +151,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "c2" if world == 1 else "c4"
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -157,6 +164,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _lib.require_gpu()
+    if world > 1:
+        run_distributed(args, L, _lib, torch, dist, rank, local_rank, world)
+        dist.destroy_process_group()
+        return
     desc, n, _ = WORKLOADS[args.workload]
     if args.n_mib:
         n = args.n_mib << 20
@@ -261,6 +272,107 @@ def main():
             "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
+    """N > 1: ONE text sharded over the N GPUs (strong scaling: the total work is fixed as N grows).
+    Distributed sample sort + prefix doubling, suffix_array_b200/dist.py; collectives = NCCL all_to_all."""
+    from suffix_array_b200 import dist as sdist, gen
+    dev = torch.device("cuda", local_rank)
+    desc, n, _ = WORKLOADS[args.workload]
+    if args.n_mib:
+        n = args.n_mib << 20
+    B, lo, hi = sdist.shard_bounds(n, rank, world)
+    end = min(n, hi + sdist.HALO)
+    if args.workload == "c4":
+        shard = gen.mixed_range(n, lo, end)      # every rank generates only its own shard
+    else:
+        shard = make_text(args.workload, n)[lo:end]
+    h_shard = torch.empty(shard.size, dtype=torch.uint8, pin_memory=True)
+    h_shard.numpy()[:] = shard
+    d_shard = h_shard.to(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    L.sab200_set_profiling(1)
+    st = {}
+    for _ in range(args.warmup):
+        sdist.dist_saca(d_shard, n, dev, stats=st)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms = pass_bytes = launches = pass_launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        sa_local, sa_off = sdist.dist_saca(d_shard, n, dev, stats=st)
+        ls = _lib.last_stats()
+        pass_ms += ls["radix_pass_ms"]
+        pass_bytes += ls["radix_pass_bytes"]
+        pass_launches += ls["radix_pass_launches"]
+        launches += ls["kernel_launches"]
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    # end to end: pinned host shard in, pinned host slice of the suffix array out
+    h_out = torch.empty(int(st["slice"] * 1.25) + 1024, dtype=torch.int32, pin_memory=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sa_local, sa_off = sdist.dist_saca(h_shard.to(dev, non_blocking=True), n, dev, stats=st)
+        if sa_local.numel() > h_out.numel():
+            h_out = torch.empty(sa_local.numel(), dtype=torch.int32, pin_memory=True)
+        h_out[:sa_local.numel()].copy_(sa_local, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    slices = sum_over_ranks(st["slice"])
+    assert int(slices) == n, "slices do not cover the suffix array"
+    a2a = sum_over_ranks(st["all_to_all_bytes"])
+    tot_pass_ms = max_over_ranks(pass_ms)
+    tot_pass_bytes = sum_over_ranks(pass_bytes)
+    tot_launches = sum_over_ranks(launches)
+    tot_pass_launches = sum_over_ranks(pass_launches)
+    peak, peak_src = hbm_peak()
+    # per-GPU achieved bandwidth of the radix passes on the slowest rank
+    achieved = (pass_bytes / 1e9) / (pass_ms / 1e3) if pass_ms > 0 else 0.0
+    achieved = -max_over_ranks(-achieved)
+    if rank == 0:
+        value = n / 1e6 / (dev_ms / 1e3)
+        print(json.dumps({
+            "metric": "sa_construction_throughput", "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8 text / u64 keys / u32 ranks", "data": "synthetic",
+            "config": {"workload": desc if not args.n_mib else "%s at %d MiB" % (args.workload, args.n_mib), "text_bytes": n,
+                       "per_gpu": "one text block-sharded over %d GPUs: sample sort of the packed keys, then prefix "
+                                  "doubling; NCCL all_to_all for keys, rank requests/answers and rank updates" % world,
+                       "l2": "inputs larger than L2 (no flush needed)", "rounds": st["rounds"], "active": st["active"],
+                       "symbols_per_key": st["symbols_per_key"], "collectives_per_step": st["collectives"],
+                       "all_to_all_bytes_per_step": int(a2a)},
+            "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (LSD radix pass, slowest rank)", "achieved": round(achieved, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "launches": int(tot_pass_launches),
+                         "share_of_step": round(tot_pass_ms / args.steps / dev_ms, 3)},
+            "e2e": {"value": round(n / 1e6 / (e2e_ms / 1e3), 2), "unit": "MB/s", "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": n + world * sdist.HALO, "d2h_bytes_per_step": 4 * n,
+                    "api": "suffix_array_b200.dist.dist_saca (pinned host shard in, pinned host SA slice out)"},
+            "cpu_baseline": None, "gpu_launches": int(tot_launches), "search": None,
+            "clocks": sampler.summary()}))
 
 
 def bench_search(L, _lib, torch, dev, text, h_sa, n, npat=2_000_000):

@@ -1,0 +1,87 @@
+/*
+ * sab200_dist.h -- per-rank step functions of the multi-GPU construction (libsab200.so).
+ *
+ * The reference has nothing distributed; this is the sharded form of the same
+ * saca() (/root/reference/src/saca.rs:9-15) for texts spread over the GPUs of one box.  One process
+ * per GPU; the exchange steps between these calls are collectives issued by the host driver
+ * (suffix_array_b200/dist.py: torch.distributed all_to_all_single / all_gather / all_reduce over
+ * NCCL on NVLink).  Every pointer below is a DEVICE pointer on `device` unless marked host; every
+ * call synchronises the library stream before returning.  Return codes as in sab200.h.
+ *
+ * Layout: rank g of P owns text positions [g*B, min((g+1)*B, n)) and their rank[] entries
+ * (B = ceil(n/P)); after the key exchange it owns a contiguous slice of the suffix array whose
+ * groups of equal keys never straddle two GPUs (splitters cut between distinct keys).
+ */
+#ifndef SAB200_DIST_H
+#define SAB200_DIST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 256-bin byte histogram of d_text[0..len) -> d_hist (256 x u64, overwritten). */
+int32_t sab200_dist_hist(const uint8_t* d_text, uint64_t len, uint64_t* d_hist, int32_t device);
+
+/* Host-only: from the GLOBAL byte histogram and text length choose the code table (codes 1..sigma,
+ * 0 = absent byte), bits per symbol b and symbols per key k (same cost model as the single-GPU path). */
+int32_t sab200_dist_plan(const uint64_t* hist256, uint64_t n, uint16_t* lut256, int32_t* b, int32_t* k);
+
+/* Keys of `count` consecutive suffixes starting at global position shard_lo.  d_text holds the text
+ * from shard_lo on: at least min(count + 64, n - shard_lo) bytes.  d_idx[j] = shard_lo + j. */
+int32_t sab200_dist_pack(const uint8_t* d_text, uint64_t shard_lo, uint64_t count, uint64_t n, const uint16_t* lut256,
+                         int32_t b, int32_t k, uint64_t* d_keys, uint32_t* d_idx, int32_t device);
+
+/* Destination rank of a key = number of splitters <= key (nsplit = P-1 host values, ascending).
+ * counts (host, P x u64) receives how many of the `count` keys go to each rank; the records are
+ * stably partitioned by destination into (d_keys_out, d_idx_out). */
+int32_t sab200_dist_partition_keys(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count,
+                                   const uint64_t* splitters, int32_t nsplit, uint64_t* d_keys_out,
+                                   uint32_t* d_idx_out, uint64_t* counts, int32_t device);
+
+/* Stable LSD radix sort of (key, payload) pairs on bits [0, key_bits).  Buffers 0 hold the input;
+ * returns 0 or 1 = which buffer pair holds the result, or < 0 on error. */
+int32_t sab200_dist_sort_pairs(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
+                               int32_t key_bits, int32_t device);
+
+/* After the local sort of this rank's slice (count records, SA positions sa_off .. sa_off+count):
+ * d_sa_local[j] = suffix of record j; d_rank_seq[j] = rank of record j (= sa_off + index of its group
+ * head); records of groups > 1 are compacted into (d_act_r1, d_act_idx); *n_active (host) = their count. */
+int32_t sab200_dist_init_ranks(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count, uint32_t sa_off,
+                               uint32_t* d_sa_local, uint32_t* d_rank_seq, uint32_t* d_act_r1, uint32_t* d_act_idx,
+                               uint64_t* n_active, int32_t device);
+
+/* Stable partition of (key, val) u32 pairs by the owner rank of text position key + add under block
+ * width B (owner = min((key + add) / B, P-1)); keys equal to 0xFFFFFFFF are dropped (they sort behind
+ * the last rank and are not counted).  counts (host, P x u64). */
+int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint32_t* d_val, uint64_t count, uint32_t add,
+                                    uint32_t B, int32_t P, uint32_t* d_key_out, uint32_t* d_val_out, uint64_t* counts,
+                                    int32_t device);
+
+/* d_rank_local[d_pos[t] - lo] = d_val[t]   (ranks arriving at their owner) */
+int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo,
+                            uint32_t* d_rank_local, int32_t device);
+/* d_out[t] = d_rank_local[d_pos[t] + add - lo]   (answering rank[i+h] requests) */
+int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo,
+                           const uint32_t* d_rank_local, uint32_t* d_out, int32_t device);
+/* d_key64[t] = (d_r1[t] << 32) | d_r2[t] */
+int32_t sab200_dist_make_keys(const uint32_t* d_r1, const uint32_t* d_r2, uint64_t count, uint64_t* d_key64,
+                              int32_t device);
+
+/* One re-ranking step on this rank's sorted active records (see rerank_kernel): newly unique suffixes
+ * are written to d_sa_local[rank - sa_off]; the rest is compacted into (d_out_r1, d_out_idx), *n_kept
+ * (host); (d_upd_idx[j], d_upd_r[j]) lists every changed rank (0xFFFFFFFF in d_upd_idx = unchanged). */
+int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint64_t m, uint32_t sa_off,
+                           uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
+                           uint32_t* d_upd_r, uint64_t* n_kept, int32_t device);
+
+/* Bracket one construction on this rank: begin() clears the counters of sab200_get_stats() (and arms
+ * per-launch event timing when sab200_set_profiling(1)); end() publishes them. */
+int32_t sab200_dist_begin(int32_t device);
+int32_t sab200_dist_end(int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAB200_DIST_H */

@@ -40,7 +40,7 @@ int sab_context_init(SabContext* c) {
     SAB_CUDA_TRY(cudaMalloc(&c->d_ghist, sizeof(u64) * SAB_MAX_PASSES * SAB_RADIX_BINS));
     SAB_CUDA_TRY(cudaMalloc(&c->d_gbase, sizeof(u64) * SAB_MAX_PASSES * SAB_RADIX_BINS));
     SAB_CUDA_TRY(cudaMalloc(&c->d_skip, sizeof(u32) * 16));
-    SAB_CUDA_TRY(cudaMallocHost(&c->h_small, sizeof(u32) * 1024));
+    SAB_CUDA_TRY(cudaMallocHost(&c->h_small, sizeof(u32) * 4096));
     SAB_CUDA_TRY(cudaMalloc(&c->d_ticket, sizeof(u32) * 4));
     SAB_CUDA_TRY(cudaMemset(c->d_ticket, 0, sizeof(u32) * 4));
     SAB_CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(u32) * 1024));
@@ -614,3 +614,5 @@ void sab200_shutdown(void) {
 }
 
 }  // extern "C"
+
+#include "sab_dist.cuh"

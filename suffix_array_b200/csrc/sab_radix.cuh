@@ -159,6 +159,7 @@ struct SplitterDigit {  // destination rank of a key: number of splitters <= key
 struct OwnerDigit {  // owner rank of text position key + add under a block distribution of width B
     u32 add, B, pmax;
     __device__ __forceinline__ u32 operator()(u32 k) const {
+        if (k == 0xffffffffu) return pmax + 1u;  // dropped record / tile padding: behind the last rank
         const u32 o = (u32)(((u64)k + add) / B);
         return o < pmax ? o : pmax;
     }

@@ -28,6 +28,11 @@
 #define SAB_SCAN_ITEMS 8
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_RANK_EMPTY 0xffffffffu
+#ifdef SAB_EMU
+#define SAB_ACTIVE_COST 30.0  // emulator runs are tiny: keep the doubling rounds exercised
+#else
+#define SAB_ACTIVE_COST 300.0
+#endif
 
 // ------------------------------------------------------------------ 1. alphabet
 __global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict__ text, u64 n, u32* __restrict__ hist) {
@@ -74,9 +79,11 @@ __device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, c
     return key;
 }
 
-// lut[c] = code of byte c (1..sigma).  key bits [0, k*b) are used.
+// lut[c] = code of byte c (1..sigma).  key bits [0, k*b) are used.  Keys are produced for positions
+// [0, count); positions >= n are past the end of the text (count < n when the buffer is a shard + halo).
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
-pack_keys_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, int b, int k, u64* __restrict__ keys) {
+pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, int b, int k,
+                 u64* __restrict__ keys) {
     SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
     s_lut[threadIdx.x] = lut[threadIdx.x];
@@ -91,7 +98,7 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut
     for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
         const int o = threadIdx.x + j * SAB_PACK_THREADS;
         const u64 i = base + o;
-        if (i < n) {
+        if (i < count) {
             u64 key = 0;
             for (int t = 0; t < k; ++t) key = (key << b) | (u64)s_code[o + t];
             keys[i] = key;
@@ -178,14 +185,18 @@ struct RankScanOp {
     }
 };
 
-// K, I: records sorted by key.  The rank of record j is r = 1 + (index of the head of j's group).
-//   sa[j+1] = I[j], sa[0] = n                         (coalesced copy)
-//   records of groups larger than one -> (act_r1, act_idx), and rank[I[j]] = r for them only
-//   dir[key >> dir_shift] = j at the first record of every directory bucket (lazy ISA, see 4b)
+// K, I: records sorted by key.  The rank of record j is r = rank_base + (index of the head of j's group)
+// (rank_base = SA position of record 0: 1 on a single GPU, the slice offset on a multi-GPU rank).
+//   sa_out[j] = I[j]                                  (coalesced copy)
+//   records of groups larger than one -> (act_r1, act_idx)
+//   rank != null:     rank[I[j]] = r for those active records only (lazy ISA, see 4b)
+//   rank_seq != null: rank_seq[j] = r for every record (multi-GPU: ranks travel to the owner of I[j])
+//   dir != null:      dir[key >> dir_shift] = j at the first record of every directory bucket
 __global__ void __launch_bounds__(SAB_SCAN_THREADS)
-init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32* __restrict__ rank,
-                  u32* __restrict__ sa, u32* __restrict__ act_r1, u32* __restrict__ act_idx, u32* __restrict__ d_count,
-                  u32* __restrict__ dir, int dir_shift, TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
+init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32 rank_base, u32* __restrict__ rank,
+                  u32* __restrict__ rank_seq, u32* __restrict__ sa_out, u32* __restrict__ act_r1,
+                  u32* __restrict__ act_idx, u32* __restrict__ d_count, u32* __restrict__ dir, int dir_shift,
+                  TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
     SAB_SHARED_VAR(u32, s_tile);
     SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
     SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
@@ -205,7 +216,7 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
         if (j < n) {
             key = K[j];
             ix = I[j];
-            sa[j + 1] = ix;
+            sa_out[j] = ix;
         }
         klo[k] = (u32)key;
         khi[k] = (u32)(key >> 32);
@@ -249,30 +260,40 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
     RankScan prefix = tile_exclusive_prefix<RankScan, RankScanOp>(st, tile, total, RankScanOp(), ident);
     u32 head_run = prefix.head > excl.head ? prefix.head : excl.head;
     u32 local = excl.cnt;  // position of this thread's first active record inside the tile's compacted output
+    u32 rs[SAB_SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
         const u64 j = j0 + k;
+        rs[k] = 0;
         if (j < n) {
             if (headbits & (1u << k)) head_run = (u32)j;
-            if (activebits & (1u << k)) {
-                const u32 r = head_run + 1u;
-                rank[idx[k]] = r;
-                s_a[SAB_PAD(local)] = r;
-                s_b[SAB_PAD(local)] = idx[k];
-                ++local;
-            }
+            rs[k] = head_run + rank_base;
+            if (rank && (activebits & (1u << k))) rank[idx[k]] = rs[k];
+        }
+    }
+    if (rank_seq) {  // rank of every record, written with coalesced stores
+#pragma unroll
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) s_a[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = rs[k];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+            const u32 o = threadIdx.x + k * SAB_SCAN_THREADS;
+            if (base + o < n) rank_seq[base + o] = s_a[SAB_PAD(o)];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        if ((j0 + k < n) && (activebits & (1u << k))) {
+            s_a[SAB_PAD(local)] = rs[k];
+            s_b[SAB_PAD(local)] = idx[k];
+            ++local;
         }
     }
     __syncthreads();
     tile_flush_compact(act_r1, prefix.cnt, total.cnt, s_a);
     tile_flush_compact(act_idx, prefix.cnt, total.cnt, s_b);
-    if (threadIdx.x == 0) {
-        if (base + SAB_SCAN_TILE >= n) *d_count = prefix.cnt + total.cnt;  // last tile
-        if (tile == 0) {
-            sa[0] = (u32)n;
-            rank[n] = 0u;
-        }
-    }
+    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= n) *d_count = prefix.cnt + total.cnt;  // last tile
 }
 
 // ------------------------------------------------------------------ 4b. lazy inverse suffix array
@@ -376,13 +397,15 @@ struct RerankScanOp {
 
 // S, I: active records sorted by (r1, r2) (S = r1<<32 | r2).  For record j:
 //   new_r1 = r1 + (head index of its new group - head index of its old group)
-//   changed rank  -> rank[I[j]] = new_r1
+//   changed rank  -> rank[I[j]] = new_r1            (rank != null: single GPU)
+//                    upd_idx[j] = I[j], upd_r[j] = new_r1, or upd_idx[j] = 0xFFFFFFFF when unchanged
+//                    (upd_idx != null: multi-GPU, the owner of rank[I[j]] is another GPU)
 //   singleton     -> sa[new_r1] = I[j] (final), dropped
 //   otherwise     -> appended to (out_r1, out_idx)
 __global__ void __launch_bounds__(SAB_SCAN_THREADS)
 rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
-              u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ d_count, TileState<RerankScan> st,
-              u32* __restrict__ ticket, u32 ticket_base) {
+              u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ upd_idx, u32* __restrict__ upd_r,
+              u32* __restrict__ d_count, TileState<RerankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
     SAB_SHARED_VAR(u32, s_tile);
     SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
     SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
@@ -450,22 +473,45 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
     RerankScan prefix = tile_exclusive_prefix<RerankScan, RerankScanOp>(st, tile, total, RerankScanOp(), ident);
     RerankScan run = RerankScanOp()(prefix, excl);
     u32 local = excl.cnt;
+    u32 nrs[SAB_SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
         const u64 j = j0 + k;
+        nrs[k] = 0;
         if (j < m) {
             if (oldbits & (1u << k)) run.ogs = (u32)j;
             if (newbits & (1u << k)) run.nhs = (u32)j;
             const u32 r1 = (u32)(key[k + 1] >> 32);
             const u32 nr = r1 + (run.nhs - run.ogs);
-            if (nr != r1) rank[idx[k]] = nr;
-            if (keepbits & (1u << k)) {
-                s_a[SAB_PAD(local)] = nr;
-                s_b[SAB_PAD(local)] = idx[k];
-                ++local;
-            } else {
-                sa[nr] = idx[k];
+            nrs[k] = nr;
+            if (rank && nr != r1) rank[idx[k]] = nr;
+            if (!(keepbits & (1u << k))) sa[nr] = idx[k];
+        }
+    }
+    if (upd_idx) {  // dense update list, written with coalesced stores
+#pragma unroll
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+            const bool changed = (j0 + k < m) && nrs[k] != (u32)(key[k + 1] >> 32);
+            s_a[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = changed ? idx[k] : 0xffffffffu;
+            s_b[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = nrs[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+            const u32 o = threadIdx.x + k * SAB_SCAN_THREADS;
+            if (base + o < m) {
+                upd_idx[base + o] = s_a[SAB_PAD(o)];
+                upd_r[base + o] = s_b[SAB_PAD(o)];
             }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        if ((j0 + k < m) && (keepbits & (1u << k))) {
+            s_a[SAB_PAD(local)] = nrs[k];
+            s_b[SAB_PAD(local)] = idx[k];
+            ++local;
         }
     }
     __syncthreads();
@@ -481,6 +527,49 @@ static inline int sab_ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
     return b;
 }
 
+// Code table and key shape from the byte histogram: codes 1..sigma in byte order (0 = absent byte /
+// past the end), b = ceil(log2(sigma+1)) bits per symbol, k symbols per key.
+static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, int* b_out, int* k_out) {
+    u32 sigma = 0;
+    double sum_p2 = 0.0;
+    for (int ch = 0; ch < 256; ++ch) {
+        if (hist[ch]) ++sigma;
+        lut[ch] = (u16)(hist[ch] ? sigma : 0);
+        const double p = n ? (double)hist[ch] / (double)n : 0.0;
+        sum_p2 += p * p;
+    }
+    int b = sab_ceil_log2_u64((u64)sigma + 1);  // codes 0..sigma
+    if (b < 1) b = 1;
+    // symbols per key: enough collision entropy to separate n random suffixes with SAB_MARGIN_BITS to
+    // spare, rounded up to whole 8-bit radix passes; never more than fit in 64 bits
+    // Cost model, in bytes moved per suffix: P radix passes of 24 B each, plus ~SAB_ACTIVE_COST bytes over
+    // all doubling rounds for every suffix still tied after the initial sort; a suffix stays tied with
+    // probability ~ n * 2^-(k*H2) (H2 = order-0 collision entropy; higher-order structure only makes the
+    // estimate optimistic, never the result wrong).
+    const int k_full = 64 / b;
+    int k = k_full;
+    const double h2 = sum_p2 < 1.0 ? -log2(sum_p2) : 0.0;
+    if (h2 > 1e-3) {
+        double best = 1e300;
+        const int p_full = (k_full * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
+        for (int p = 1; p <= p_full; ++p) {
+            int kp = p * SAB_RADIX_BITS / b;
+            if (kp > k_full) kp = k_full;
+            if (kp < 1) continue;
+            double tied = exp2(log2((double)n) - (double)kp * h2);
+            if (tied > 1.0) tied = 1.0;
+            const double cost = 24.0 * p + SAB_ACTIVE_COST * tied;
+            if (cost < best - 1e-9) {
+                best = cost;
+                k = kp;
+            }
+        }
+    }
+    *sigma_out = sigma;
+    *b_out = b;
+    *k_out = k;
+}
+
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
@@ -491,11 +580,6 @@ static inline size_t sab_saca_workspace_bytes(u64 n) {
            sab_align_up((((size_t)1 << dir_bits) + 8) * 4, 256) + 4096;
 }
 
-#ifdef SAB_EMU
-#define SAB_ACTIVE_COST 30.0  // emulator runs are tiny: keep the doubling rounds exercised
-#else
-#define SAB_ACTIVE_COST 300.0
-#endif
 
 // d_text: n bytes; d_sa: n+1 u32; both device memory.  Work is enqueued on c->stream and the
 // stream is synchronised before returning.
@@ -539,39 +623,11 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     memcpy(h_hist, c->h_small + 64, sizeof(h_hist));
     u16 lut[256];
     u32 sigma = 0;
-    double sum_p2 = 0.0;
-    for (int ch = 0; ch < 256; ++ch) {
-        if (h_hist[ch]) ++sigma;
-        lut[ch] = (u16)(h_hist[ch] ? sigma : 0);
-        const double p = (double)h_hist[ch] / (double)n;
-        sum_p2 += p * p;
-    }
-    int b = sab_ceil_log2_u64((u64)sigma + 1);  // codes 0..sigma
-    if (b < 1) b = 1;
-    // symbols per key: enough collision entropy to separate n random suffixes with SAB_MARGIN_BITS to
-    // spare, rounded up to whole 8-bit radix passes; never more than fit in 64 bits
-    // Cost model, in bytes moved per suffix: P radix passes of 24 B each, plus ~SAB_ACTIVE_COST bytes over
-    // all doubling rounds for every suffix still tied after the initial sort; a suffix stays tied with
-    // probability ~ n * 2^-(k*H2) (H2 = order-0 collision entropy; higher-order structure only makes the
-    // estimate optimistic, never the result wrong).
-    const int k_full = 64 / b;
-    int k = k_full;
-    const double h2 = sum_p2 < 1.0 ? -log2(sum_p2) : 0.0;
-    if (h2 > 1e-3) {
-        double best = 1e300;
-        const int p_full = (k_full * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
-        for (int p = 1; p <= p_full; ++p) {
-            int kp = p * SAB_RADIX_BITS / b;
-            if (kp > k_full) kp = k_full;
-            if (kp < 1) continue;
-            double tied = exp2(log2((double)n) - (double)kp * h2);
-            if (tied > 1.0) tied = 1.0;
-            const double cost = 24.0 * p + SAB_ACTIVE_COST * tied;
-            if (cost < best - 1e-9) {
-                best = cost;
-                k = kp;
-            }
-        }
+    int b = 1, k = 1;
+    {
+        u64 h64[256];
+        for (int ch = 0; ch < 256; ++ch) h64[ch] = h_hist[ch];
+        sab_plan_alphabet(h64, n, lut, &sigma, &b, &k);
     }
     S.sigma = sigma;
     S.bits_per_symbol = (u32)b;
@@ -581,8 +637,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
 
     // 2. packed keys
-    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, (const u16*)d_lut,
-               b, k, buf.k[0]);
+    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
+               (const u16*)d_lut, b, k, buf.k[0]);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     S.kernel_launches++;
@@ -603,13 +659,16 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     if (dir_bits < 1) dir_bits = 1;
     const int dir_shift = key_bits - dir_bits;
     u32* dir = sab_arena_take<u32>(c, ((size_t)1 << dir_bits) + 8);
-    SAB_CUDA_TRY(cudaMemsetAsync(rank, 0xff, (n + 1) * sizeof(u32), st));
+    SAB_CUDA_TRY(cudaMemsetAsync(rank, 0xff, n * sizeof(u32), st));
+    SAB_CUDA_TRY(cudaMemsetAsync(rank + n, 0, sizeof(u32), st));  // the empty suffix has rank 0
+    c->h_small[32] = (u32)n;
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_sa, c->h_small + 32, sizeof(u32), cudaMemcpyHostToDevice, st));  // sa[0] = n
     {
         const u64 tiles = div_up64(n, SAB_SCAN_TILE);
         TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
         sab_prof_begin(c, 3);
-        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, n, rank, d_sa, r1buf,
-                   act_idx, d_m, dir, dir_shift, ts, c->d_ticket, c->ticket_host);
+        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, n, 1u, rank,
+                   (u32*)nullptr, d_sa + 1, r1buf, act_idx, d_m, dir, dir_shift, ts, c->d_ticket, c->ticket_host);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         c->ticket_host += (u32)tiles;
@@ -679,8 +738,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
             sab_prof_begin(c, 3);
             SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)rb.k[rb.cur],
-                       (const u32*)rb.v[rb.cur], m, rank, d_sa, r1buf, rb.v[rb.cur ^ 1], d_m, ts, c->d_ticket,
-                       c->ticket_host);
+                       (const u32*)rb.v[rb.cur], m, rank, d_sa, r1buf, rb.v[rb.cur ^ 1], (u32*)nullptr, (u32*)nullptr, d_m,
+                       ts, c->d_ticket, c->ticket_host);
             sab_prof_end(c);
             SAB_LAUNCH_CHECK();
             c->ticket_host += (u32)tiles;

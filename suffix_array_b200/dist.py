@@ -1,0 +1,282 @@
+"""Multi-GPU suffix-array construction: one process per GPU, torch.distributed for the plumbing.
+
+The reference has nothing distributed; this is the sharded form of saca()
+(/root/reference/src/saca.rs:9-15) for texts spread over the GPUs of one box:
+distributed sample sort on the packed keys, then prefix doubling with two exchange steps per round.
+
+    rank g owns text positions [g*B, (g+1)*B) and their rank[] entries            (B = ceil(n/P))
+    1  byte histogram            all_reduce             -> common code table, key shape
+    2  pack keys of own positions; P-1 splitters from an all_gather'ed key sample
+    3  partition by destination (onesweep kernel, digit = #splitters <= key)       all_to_all (key, i)
+    4  local radix sort -> this rank's contiguous slice of the suffix array; equal keys always land
+       on one GPU, so groups never straddle GPUs and all re-ranking is local
+    5  ranks to the owners of i                                                     all_to_all (i, rank)
+    6  rounds h = k, 2k, ...:  requests i+h to their owners, answers back           2 x all_to_all
+       local sort by (r1, r2), local re-rank, changed ranks to their owners         all_to_all
+
+Every compute step is a CUDA kernel of libsab200 reached through include/sab200_dist.h; the
+collectives are torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests, where the
+"device" is the SIMT-emulator build).  Tensors are used as untyped device buffers.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+HALO = 64
+
+
+def shard_bounds(n, rank, world):
+    B = max(1, -(-n // world))
+    lo = min(rank * B, n)
+    hi = min(lo + B, n)
+    return B, lo, hi
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+
+
+def _bind(L):
+    if getattr(L, "_sab_dist_bound", False):
+        return L
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    sig = {
+        "sab200_dist_hist": [vp, u64, vp, i32],
+        "sab200_dist_plan": [vp, u64, vp, C.POINTER(i32), C.POINTER(i32)],
+        "sab200_dist_pack": [vp, u64, u64, u64, vp, i32, i32, vp, vp, i32],
+        "sab200_dist_partition_keys": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
+        "sab200_dist_sort_pairs": [vp, vp, vp, vp, u64, i32, i32],
+        "sab200_dist_init_ranks": [vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64), i32],
+        "sab200_dist_partition_owner": [vp, vp, u64, u32, u32, i32, vp, vp, vp, i32],
+        "sab200_dist_scatter": [vp, vp, u64, u32, vp, i32],
+        "sab200_dist_gather": [vp, u64, u32, u32, vp, vp, i32],
+        "sab200_dist_make_keys": [vp, vp, u64, vp, i32],
+        "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
+        "sab200_dist_begin": [i32],
+        "sab200_dist_end": [i32],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = i32
+    L._sab_dist_bound = True
+    return L
+
+
+class _Ctx:
+    def __init__(self, device, group):
+        self.L = _bind(_lib.lib())
+        self.device = torch.device(device)
+        self.dev = self.device.index if self.device.type == "cuda" else 0
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.P = dist.get_world_size(group)
+        self.a2a_bytes = 0
+        self.collectives = 0
+
+    def check(self, rc, what):
+        if rc < 0:
+            _lib.check(rc, what)
+        return rc
+
+    def sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def empty(self, n, dtype):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
+
+    def exchange_counts(self, send_counts):
+        sc = torch.tensor([int(x) for x in send_counts], dtype=torch.int64, device=self.device)
+        rc = torch.empty(self.P, dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        self.collectives += 1
+        return [int(x) for x in rc.tolist()]
+
+    def all_to_all(self, buf, send_counts, recv_counts):
+        """buf: 1-D tensor laid out rank-major with send_counts elements per destination."""
+        out = self.empty(sum(recv_counts), buf.dtype)
+        src = buf[:sum(send_counts)]
+        dist.all_to_all_single(out, src.contiguous(), output_split_sizes=list(recv_counts),
+                               input_split_sizes=list(send_counts), group=self.group)
+        self.sync()
+        self.a2a_bytes += src.numel() * src.element_size()
+        self.collectives += 1
+        return out
+
+
+def _to_owner(cx, keys, vals, count, add, B):
+    """Stable partition of (keys, vals) by the owner of position keys+add; returns the partitioned
+    buffers and the per-destination counts (records whose key is 0xFFFFFFFF are dropped)."""
+    kp = cx.empty(count, torch.int32)
+    vp = cx.empty(count, torch.int32)
+    cnt = np.zeros(cx.P, dtype=np.uint64)
+    cx.check(cx.L.sab200_dist_partition_owner(_p(keys), _p(vals), count, add, B, cx.P, _p(kp), _p(vp),
+                                              cnt.ctypes.data_as(C.c_void_p), cx.dev), "sab200_dist_partition_owner")
+    return kp, vp, [int(x) for x in cnt]
+
+
+def _send_ranks(cx, idx, ranks, count, B, lo, rank_local):
+    """rank[idx[t]] = ranks[t] on the GPU that owns text position idx[t]."""
+    kp, vp, send = _to_owner(cx, idx, ranks, count, 0, B)
+    recv = cx.exchange_counts(send)
+    ri = cx.all_to_all(kp, send, recv)
+    rr = cx.all_to_all(vp, send, recv)
+    cx.check(cx.L.sab200_dist_scatter(_p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev), "sab200_dist_scatter")
+
+
+def dist_saca(shard, n, device, group=None, stats=None):
+    """Builds the suffix array of a text of n bytes spread over the ranks of `group`.
+
+    shard: uint8 numpy array or tensor with this rank's text positions [lo, hi) followed by up to HALO
+    bytes of the next shard (text[lo : min(n, hi + HALO)], see shard_bounds).
+    Returns (sa_local, sa_off): this rank's slice of the suffix array -- int32 tensor holding u32
+    suffix indices for SA positions [sa_off, sa_off + len) -- the sentinel entry sa[0] = n is implied
+    (rank 0's slice starts at position 1)."""
+    cx = _Ctx(device, group)
+    L, P, rank = cx.L, cx.P, cx.rank
+    if n > _lib.MAX_LENGTH:
+        raise ValueError("text longer than MAX_LENGTH")
+    B, lo, hi = shard_bounds(n, rank, P)
+    count = hi - lo
+    cx.check(L.sab200_dist_begin(cx.dev), "sab200_dist_begin")
+    d_text = torch.as_tensor(shard, dtype=torch.uint8).to(cx.device)
+    need = min(count + HALO, n - lo)
+    if d_text.numel() < need:
+        raise ValueError("shard too short: %d bytes, need %d (own positions + halo)" % (d_text.numel(), need))
+    # 1. common alphabet / key shape
+    d_hist = torch.zeros(256, dtype=torch.int64, device=cx.device)
+    cx.check(L.sab200_dist_hist(_p(d_text), count, _p(d_hist), cx.dev), "sab200_dist_hist")
+    dist.all_reduce(d_hist, group=cx.group)
+    hist = d_hist.cpu().numpy().astype(np.uint64)
+    lut = np.zeros(256, dtype=np.uint16)
+    b, k = C.c_int32(), C.c_int32()
+    cx.check(L.sab200_dist_plan(hist.ctypes.data_as(C.c_void_p), n, lut.ctypes.data_as(C.c_void_p), C.byref(b), C.byref(k)),
+             "sab200_dist_plan")
+    b, k = b.value, k.value
+    key_bits = b * k
+    # 2. keys of own positions, splitters from a sample
+    keys = cx.empty(count, torch.int64)
+    idx = cx.empty(count, torch.int32)
+    cx.check(L.sab200_dist_pack(_p(d_text), lo, count, n, lut.ctypes.data_as(C.c_void_p), b, k, _p(keys), _p(idx), cx.dev),
+             "sab200_dist_pack")
+    S = 2048
+    sample = torch.zeros(S + 1, dtype=torch.int64, device=cx.device)
+    if count:
+        step = max(1, count // S)
+        s = keys[::step][:S]
+        sample[:s.numel()] = s
+        sample[S] = s.numel()
+    gathered = [torch.empty_like(sample) for _ in range(P)]
+    dist.all_gather(gathered, sample, group=cx.group)
+    pool = np.concatenate([g.cpu().numpy()[:int(g[S])] for g in gathered]).view(np.uint64)
+    pool.sort()
+    splitters = np.zeros(max(P - 1, 1), dtype=np.uint64)
+    for i in range(P - 1):
+        splitters[i] = pool[min(pool.size - 1, (i + 1) * pool.size // P)] if pool.size else 0
+    # 3. partition by destination, exchange
+    kp = cx.empty(count, torch.int64)
+    ip = cx.empty(count, torch.int32)
+    cnt = np.zeros(P, dtype=np.uint64)
+    cx.check(L.sab200_dist_partition_keys(_p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
+                                          cnt.ctypes.data_as(C.c_void_p), cx.dev), "sab200_dist_partition_keys")
+    send = [int(x) for x in cnt]
+    recv = cx.exchange_counts(send)
+    k0 = cx.all_to_all(kp, send, recv)
+    v0 = cx.all_to_all(ip, send, recv)
+    del keys, idx, kp, ip
+    R = k0.numel()
+    # 4. local sort: this rank's slice of the suffix array
+    k1 = cx.empty(R, torch.int64)
+    v1 = cx.empty(R, torch.int32)
+    which = cx.check(L.sab200_dist_sort_pairs(_p(k0), _p(k1), _p(v0), _p(v1), R, key_bits, cx.dev), "sab200_dist_sort_pairs")
+    ks, vs = (k0, v0) if which == 0 else (k1, v1)
+    sizes = torch.zeros(P, dtype=torch.int64, device=cx.device)
+    sizes[rank] = R
+    dist.all_reduce(sizes, group=cx.group)
+    sizes = [int(x) for x in sizes.tolist()]
+    sa_off = 1 + sum(sizes[:rank])
+    sa_local = cx.empty(R, torch.int32)
+    rank_seq = cx.empty(R, torch.int32)
+    act_r1 = cx.empty(R, torch.int32)
+    act_idx = cx.empty(R, torch.int32)
+    m = C.c_uint64()
+    cx.check(L.sab200_dist_init_ranks(_p(ks), _p(vs), R, sa_off, _p(sa_local), _p(rank_seq), _p(act_r1), _p(act_idx),
+                                      C.byref(m), cx.dev), "sab200_dist_init_ranks")
+    m = m.value
+    # 5. every rank travels to the owner of its text position
+    rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n (rank 0) if owned
+    _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
+    del ks, vs, k0, k1, v0, v1, rank_seq
+    # 6. doubling rounds
+    rank_bits = max(1, int(n + 1).bit_length())
+    cur_r1, cur_idx = act_r1[:m], act_idx[:m]
+    h = k
+    rounds = 0
+    active = []
+    while True:
+        tot = torch.tensor([m], dtype=torch.int64, device=cx.device)
+        dist.all_reduce(tot, group=cx.group)
+        tot = int(tot.item())
+        active.append(tot)
+        if tot == 0:
+            break
+        rounds += 1
+        if h > n or rounds > 64:
+            raise RuntimeError("prefix doubling did not converge")
+        # requests i+h to the owners, answers back in the same order
+        ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, B)
+        recv = cx.exchange_counts(send)
+        q = cx.all_to_all(ipart, send, recv)
+        ans = cx.empty(q.numel(), torch.int32)
+        cx.check(L.sab200_dist_gather(_p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev), "sab200_dist_gather")
+        r2 = cx.all_to_all(ans, recv, send)
+        key64 = cx.empty(m, torch.int64)
+        cx.check(L.sab200_dist_make_keys(_p(rpart), _p(r2), m, _p(key64), cx.dev), "sab200_dist_make_keys")
+        key_tmp = cx.empty(m, torch.int64)
+        idx_tmp = cx.empty(m, torch.int32)
+        which = cx.check(L.sab200_dist_sort_pairs(_p(key64), _p(key_tmp), _p(ipart), _p(idx_tmp), m, 32 + rank_bits, cx.dev),
+                         "sab200_dist_sort_pairs")
+        sk, si = (key64, ipart) if which == 0 else (key_tmp, idx_tmp)
+        out_r1 = cx.empty(m, torch.int32)
+        out_idx = cx.empty(m, torch.int32)
+        upd_idx = cx.empty(m, torch.int32)
+        upd_r = cx.empty(m, torch.int32)
+        kept = C.c_uint64()
+        cx.check(L.sab200_dist_rerank(_p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
+                                      C.byref(kept), cx.dev), "sab200_dist_rerank")
+        _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
+        m = kept.value
+        cur_r1, cur_idx = out_r1[:m], out_idx[:m]
+        h *= 2
+    cx.check(L.sab200_dist_end(cx.dev), "sab200_dist_end")
+    if stats is not None:
+        stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
+                      "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives})
+    return sa_local, sa_off
+
+
+def gather_sa(sa_local, n, group=None):
+    """Assembles the full suffix array (n+1 entries incl. the sentinel) on every rank (tests / small n)."""
+    P = dist.get_world_size(group)
+    size = torch.tensor([sa_local.numel()], dtype=torch.int64, device=sa_local.device)
+    sizes = [torch.empty_like(size) for _ in range(P)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes + [1])
+    pad = torch.zeros(mx, dtype=torch.int32, device=sa_local.device)
+    pad[:sa_local.numel()] = sa_local
+    parts = [torch.empty_like(pad) for _ in range(P)]
+    dist.all_gather(parts, pad, group=group)
+    out = np.empty(n + 1, dtype=np.uint32)
+    out[0] = n
+    pos = 1
+    for p, s in zip(parts, sizes):
+        out[pos:pos + s] = p[:s].cpu().numpy().view(np.uint32)
+        pos += s
+    assert pos == n + 1
+    return out

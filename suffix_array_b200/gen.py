@@ -99,49 +99,108 @@ _LETTER_W = np.array([12.7, 9.1, 8.2, 7.5, 7.0, 6.7, 6.3, 6.1, 6.0, 4.3, 4.0, 2.
                       1.9, 1.5, 1.0, 0.8, 0.15, 0.15, 0.1, 0.07])
 
 
-def english_like(n: int, seed: int = SEED_C4, vocab: int = 4096) -> np.ndarray:
-    """Words from a synthetic Zipf(1.0) vocabulary (lengths 2..10, letters by English frequency),
-    joined by single spaces (imitates Pizza&Chili english)."""
-    if n == 0:
-        return np.empty(0, dtype=np.uint8)
-    r = splitmix64(seed ^ 0x0E0E0E0E, 0, vocab * 11)
-    lens = (2 + (r[:vocab] % np.uint64(9))).astype(np.int64)
-    cum = np.cumsum(_LETTER_W / _LETTER_W.sum())
-    u = (r[vocab:vocab * 11] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
-    letters = _LETTERS[np.minimum(np.searchsorted(cum, u), 25)].reshape(vocab, 10)
-    padded = np.full((vocab, 11), ord(" "), dtype=np.uint8)
-    padded[:, :10] = letters
-    valid = np.zeros((vocab, 11), dtype=bool)
-    for L in range(2, 11):
-        rows = lens == L
-        valid[rows, :L] = True
-        valid[rows, L] = True  # the separating space
-        padded[rows, L] = ord(" ")
-    zipf = 1.0 / np.arange(1, vocab + 1)
-    zcum = np.cumsum(zipf / zipf.sum())
-    out = np.empty(n, dtype=np.uint8)
+_ENG_BLOCK = 1 << 20
+_ENG_CACHE = {}
+
+
+def _english_tables(seed: int, vocab: int):
+    key = (seed, vocab)
+    if key not in _ENG_CACHE:
+        r = splitmix64(seed ^ 0x0E0E0E0E, 0, vocab * 11)
+        lens = (2 + (r[:vocab] % np.uint64(9))).astype(np.int64)
+        cum = np.cumsum(_LETTER_W / _LETTER_W.sum())
+        u = (r[vocab:vocab * 11] >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+        letters = _LETTERS[np.minimum(np.searchsorted(cum, u), 25)].reshape(vocab, 10)
+        padded = np.full((vocab, 11), ord(" "), dtype=np.uint8)
+        padded[:, :10] = letters
+        valid = np.zeros((vocab, 11), dtype=bool)
+        for L in range(2, 11):
+            rows = lens == L
+            valid[rows, :L] = True
+            valid[rows, L] = True  # the separating space
+            padded[rows, L] = ord(" ")
+        zipf = 1.0 / np.arange(1, vocab + 1)
+        zcum = np.cumsum(zipf / zipf.sum())
+        _ENG_CACHE[key] = (padded, valid, zcum)
+    return _ENG_CACHE[key]
+
+
+def _english_block(seed: int, vocab: int, j: int) -> np.ndarray:
+    """Block j (1 MiB) of the English-like text: a pure function of (seed, j)."""
+    padded, valid, zcum = _english_tables(seed, vocab)
+    out = np.empty(_ENG_BLOCK, dtype=np.uint8)
     pos = 0
     w = 0
-    chunk = 1 << 21
-    while pos < n:
-        rr = splitmix64(seed, w, chunk)
+    chunk = 1 << 18
+    bseed = (seed * 0x9E3779B1 + 0x632BE5AB * (j + 1)) & 0xFFFFFFFFFFFFFFFF
+    while pos < _ENG_BLOCK:
+        rr = splitmix64(bseed, w, chunk)
         w += chunk
         uu = (rr >> np.uint64(11)).astype(np.float64) / float(1 << 53)
         sel = np.minimum(np.searchsorted(zcum, uu), vocab - 1)
         piece = padded[sel].ravel()[valid[sel].ravel()]
-        take = min(piece.size, n - pos)
+        take = min(piece.size, _ENG_BLOCK - pos)
         out[pos:pos + take] = piece[:take]
         pos += take
     return out
 
 
+def english_like_range(lo: int, hi: int, seed: int = SEED_C4, vocab: int = 4096) -> np.ndarray:
+    """Bytes [lo, hi) of the (unbounded) English-like text: words from a synthetic Zipf(1.0) vocabulary
+    (lengths 2..10, letters by English frequency) joined by single spaces, generated in independent
+    1 MiB blocks so any range can be produced without the rest (imitates Pizza&Chili english)."""
+    out = np.empty(max(hi - lo, 0), dtype=np.uint8)
+    p = lo
+    while p < hi:
+        j = p // _ENG_BLOCK
+        blk = _english_block(seed, vocab, j)
+        a = p - j * _ENG_BLOCK
+        take = min(_ENG_BLOCK - a, hi - p)
+        out[p - lo:p - lo + take] = blk[a:a + take]
+        p += take
+    return out
+
+
+def english_like(n: int, seed: int = SEED_C4, vocab: int = 4096) -> np.ndarray:
+    return english_like_range(0, n, seed, vocab)
+
+
+def uniform_range(lo: int, hi: int, seed: int = SEED_C1) -> np.ndarray:
+    """Bytes [lo, hi) of the uniform byte stream of `seed`."""
+    w0 = lo // 8
+    w1 = (hi + 7) // 8
+    out = np.empty(max(hi - lo, 0), dtype=np.uint8)
+    pos = lo
+    w = w0
+    while w < w1:
+        c = min(1 << 22, w1 - w)
+        b = splitmix64(seed, w, c).view(np.uint8)
+        a = max(pos - w * 8, 0)
+        take = min(b.size - a, hi - pos)
+        out[pos - lo:pos - lo + take] = b[a:a + take]
+        pos += take
+        w += c
+    return out
+
+
+def mixed_range(n: int, lo: int, hi: int, seed: int = SEED_C4) -> np.ndarray:
+    """Bytes [lo, hi) of the C4 text of total length n: first half uniform bytes, second half
+    English-like text.  Every rank of a multi-GPU run generates just its own shard."""
+    h = n // 2
+    hi = min(hi, n)
+    out = np.empty(max(hi - lo, 0), dtype=np.uint8)
+    if lo < h:
+        e = min(hi, h)
+        out[:e - lo] = uniform_range(lo, e, seed)
+    if hi > h:
+        s0 = max(lo, h)
+        out[s0 - lo:] = english_like_range(s0 - h, hi - h, seed)
+    return out
+
+
 def mixed(n: int, seed: int = SEED_C4) -> np.ndarray:
     """C4: first half uniform bytes, second half English-like text."""
-    h = n // 2
-    out = np.empty(n, dtype=np.uint8)
-    _stream_bytes(seed, h, out[:h])
-    out[h:] = english_like(n - h, seed)
-    return out
+    return mixed_range(n, 0, n, seed)
 
 
 def patterns(text: np.ndarray, count: int, seed: int = SEED_C5, min_len: int = 8, max_len: int = 64,
