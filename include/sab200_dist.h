@@ -25,7 +25,9 @@ extern "C" {
 int32_t sab200_dist_hist(const uint8_t* d_text, uint64_t len, uint64_t* d_hist, int32_t device);
 
 /* Host-only: from the GLOBAL byte histogram and text length choose the code table (codes 1..sigma,
- * 0 = absent byte), bits per symbol b and symbols per key k (same cost model as the single-GPU path). */
+ * 0 = absent byte), the key radix b = sigma + 1 and the symbols per key k (same cost model as the
+ * single-GPU path).  A key is the mixed-radix number of the first k codes; it needs
+ * bit_length(b^k - 1) bits. */
 int32_t sab200_dist_plan(const uint64_t* hist256, uint64_t n, uint16_t* lut256, int32_t* b, int32_t* k);
 
 /* Keys of `count` consecutive suffixes starting at global position shard_lo.  d_text holds the text

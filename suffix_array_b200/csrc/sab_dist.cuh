@@ -92,10 +92,10 @@ extern "C" int32_t sab200_dist_hist(const uint8_t* d_text, uint64_t len, uint64_
 
 extern "C" int32_t sab200_dist_plan(const uint64_t* hist256, uint64_t n, uint16_t* lut256, int32_t* b, int32_t* k) {
     if (!hist256 || !lut256 || !b || !k) return SAB_ERR_ARGS;
-    u32 sigma = 0;
-    int bb = 1, kk = 1;
-    sab_plan_alphabet(hist256, n, lut256, &sigma, &bb, &kk);
-    *b = bb;
+    u32 sigma = 0, base = 2;
+    int kk = 1, bits = 1;
+    sab_plan_alphabet(hist256, n, lut256, &sigma, &base, &kk, &bits);
+    *b = (int32_t)base;
     *k = kk;
     return SAB_OK;
 }
@@ -105,7 +105,7 @@ extern "C" int32_t sab200_dist_pack(const uint8_t* d_text, uint64_t shard_lo, ui
                                     int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
-    if (shard_lo > n || b < 1 || k < 1 || k * b > 64) return SAB_ERR_ARGS;
+    if (shard_lo > n || b < 2 || k < 1 || k > 64) return SAB_ERR_ARGS;
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = c->stream;
     if (count == 0) return SAB_OK;
@@ -113,7 +113,7 @@ extern "C" int32_t sab200_dist_pack(const uint8_t* d_text, uint64_t shard_lo, ui
     memcpy(c->h_small + 384, lut256, 256 * sizeof(u16));
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, 256 * sizeof(u16), cudaMemcpyHostToDevice, st));
     SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n - shard_lo, count,
-               (const u16*)d_lut, (int)b, (int)k, d_keys);
+               (const u16*)d_lut, (u32)b, (int)k, d_keys);
     SAB_LAUNCH_CHECK();
     SAB_LAUNCH(iota_base_kernel, (unsigned)div_up64(count, 256), 256, 0, st, d_idx, count, (u32)shard_lo);
     SAB_LAUNCH_CHECK();
@@ -175,9 +175,8 @@ extern "C" int32_t sab200_dist_init_ranks(const uint64_t* d_keys, const uint32_t
     TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
     u32* d_m = c->d_counters;
     SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, d_keys, d_idx, count, sa_off, (u32*)nullptr,
-               d_rank_seq, d_sa_local, d_act_r1, d_act_idx, d_m, (u32*)nullptr, 0, ts, c->d_ticket, c->ticket_host);
+               d_rank_seq, d_sa_local, d_act_r1, d_act_idx, d_m, (u32*)nullptr, 0, ts);
     SAB_LAUNCH_CHECK();
-    c->ticket_host += (u32)tiles;
     SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
     *n_active = c->h_small[0];
@@ -261,9 +260,8 @@ extern "C" int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d
     // ranks are global SA positions: index the local slice through a pointer shifted by the slice offset
     u32* sa_shifted = d_sa_local - (size_t)sa_off;
     SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, d_key64, d_idx, m, (u32*)nullptr, sa_shifted, d_out_r1,
-               d_out_idx, d_upd_idx, d_upd_r, d_m, ts, c->d_ticket, c->ticket_host);
+               d_out_idx, d_upd_idx, d_upd_r, d_m, ts);
     SAB_LAUNCH_CHECK();
-    c->ticket_host += (u32)tiles;
     SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
     *n_kept = c->h_small[0];

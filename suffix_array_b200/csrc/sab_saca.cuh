@@ -3,8 +3,8 @@
 //
 //   1. alphabet_hist        256-bin byte histogram -> sigma, code LUT (codes 1..sigma; 0 = past the end),
 //                           collision entropy H2 -> how many symbols the initial key needs
-//   2. pack_keys            key[i] = first k codes of suffix i, MSB first, b = ceil(log2(sigma+1)) bits
-//                           each.  Code 0 past the end makes a proper prefix sort first and keeps real
+//   2. pack_keys            key[i] = first k codes of suffix i as a mixed-radix number in base sigma+1
+//                           (most significant first).  Code 0 past the end makes a proper prefix sort first and keeps real
 //                           0x00 bytes distinct from padding.  k = whole radix passes chosen by a
 //                           cost model (passes vs expected ties from the collision entropy H2), <= 64 bits.
 //   3. radix sort (key, i)  sab_sort.cuh
@@ -69,38 +69,38 @@ __global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict
 #define SAB_PACK_TILE (SAB_PACK_THREADS * SAB_PACK_ITEMS)
 
 // key of the suffix starting at i: k codes, MSB first, code 0 beyond the end of the text
-__device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, int b, int k,
+__device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, u32 base, int k,
                                            u64 i) {
     u64 key = 0;
     for (int t = 0; t < k; ++t) {
         const u64 p = i + (u64)t;
-        key = (key << b) | (u64)(p < n ? lut[text[p]] : (u16)0);
+        key = key * base + (u64)(p < n ? lut[text[p]] : (u16)0);
     }
     return key;
 }
 
-// lut[c] = code of byte c (1..sigma).  key bits [0, k*b) are used.  Keys are produced for positions
+// lut[c] = code of byte c (1..sigma); key = sum code_t * base^(k-1-t), base = sigma + 1.  Keys are produced for positions
 // [0, count); positions >= n are past the end of the text (count < n when the buffer is a shard + halo).
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
-pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, int b, int k,
+pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k,
                  u64* __restrict__ keys) {
     SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
-    const u64 base = (u64)blockIdx.x * SAB_PACK_TILE;
+    const u64 tile0 = (u64)blockIdx.x * SAB_PACK_TILE;
     for (int o = threadIdx.x; o < SAB_PACK_TILE + 64; o += SAB_PACK_THREADS) {
-        const u64 i = base + o;
+        const u64 i = tile0 + o;
         s_code[o] = i < n ? s_lut[text[i]] : (u16)0;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
         const int o = threadIdx.x + j * SAB_PACK_THREADS;
-        const u64 i = base + o;
+        const u64 i = tile0 + o;
         if (i < count) {
             u64 key = 0;
-            for (int t = 0; t < k; ++t) key = (key << b) | (u64)s_code[o + t];
+            for (int t = 0; t < k; ++t) key = key * radix + (u64)s_code[o + t];
             keys[i] = key;
         }
     }
@@ -166,6 +166,20 @@ __device__ __forceinline__ void tile_striped_to_blocked(u32 (&v)[SAB_SCAN_ITEMS]
     __syncthreads();
 }
 
+// key[1..ITEMS] hold this thread's (blocked) items; fills key[0] / key[ITEMS+1] with the elements just
+// before / after them: neighbours inside the tile come from shared memory, the two elements outside the
+// tile (edge_prev for thread 0, edge_next for the last thread) were fetched with the tile's first loads.
+__device__ __forceinline__ void tile_neighbor_keys(u64 (&key)[SAB_SCAN_ITEMS + 2], u64 edge_prev, u64 edge_next) {
+    SAB_SHARED_ARRAY(u64, s_first, SAB_SCAN_THREADS);
+    SAB_SHARED_ARRAY(u64, s_last, SAB_SCAN_THREADS);
+    s_first[threadIdx.x] = key[1];
+    s_last[threadIdx.x] = key[SAB_SCAN_ITEMS];
+    __syncthreads();
+    key[0] = threadIdx.x > 0 ? s_last[threadIdx.x - 1] : edge_prev;
+    key[SAB_SCAN_ITEMS + 1] = threadIdx.x < SAB_SCAN_THREADS - 1 ? s_first[threadIdx.x + 1] : edge_next;
+    __syncthreads();
+}
+
 // writes `count` compacted words staged at s[SAB_PAD(0..count)] to g[out_base ..] with coalesced stores
 __device__ __forceinline__ void tile_flush_compact(u32* __restrict__ g, u64 out_base, u32 count, const u32* __restrict__ s) {
     for (u32 o = threadIdx.x; o < count; o += SAB_SCAN_THREADS) g[out_base + o] = s[SAB_PAD(o)];
@@ -196,15 +210,14 @@ __global__ void __launch_bounds__(SAB_SCAN_THREADS)
 init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32 rank_base, u32* __restrict__ rank,
                   u32* __restrict__ rank_seq, u32* __restrict__ sa_out, u32* __restrict__ act_r1,
                   u32* __restrict__ act_idx, u32* __restrict__ d_count, u32* __restrict__ dir, int dir_shift,
-                  TileState<RankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
-    SAB_SHARED_VAR(u32, s_tile);
+                  TileState<RankScan> st) {
     SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
     SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
-    const u32 tile = s_tile;
+    const u32 tile = blockIdx.x;  // 1-D grids are dispatched in block order: predecessors have started
     const u64 base = (u64)tile * SAB_SCAN_TILE;
     const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+    const u64 edge_prev = (threadIdx.x == 0 && base > 0) ? K[base - 1] : 0ull;
+    const u64 edge_next = (threadIdx.x == SAB_SCAN_THREADS - 1 && base + SAB_SCAN_TILE < n) ? K[base + SAB_SCAN_TILE] : 0ull;
 
     // ---- coalesced loads (striped), sa copy on the way, then exchange to blocked
     u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
@@ -228,8 +241,7 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
     u64 key[SAB_SCAN_ITEMS + 2];  // key[0] = predecessor, key[ITEMS+1] = successor
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
-    key[0] = (j0 > 0 && j0 - 1 < n) ? K[j0 - 1] : 0ull;
-    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < n) ? K[j0 + SAB_SCAN_ITEMS] : 0ull;
+    tile_neighbor_keys(key, edge_prev, edge_next);
 
     RankScan mine;
     mine.head = 0;
@@ -309,11 +321,12 @@ struct LazyIsa {
     const u64* sorted_keys;  // null -> rank[] is complete
     const u32* dir;
     u64 n;
-    int b, k, dir_shift;
+    u32 base;
+    int k, dir_shift;
 };
 
 __device__ __forceinline__ u32 lazy_rank_lookup(const LazyIsa& z, u64 t) {
-    const u64 key = pack_key_at(z.text, z.n, z.lut, z.b, z.k, t);
+    const u64 key = pack_key_at(z.text, z.n, z.lut, z.base, z.k, t);
     u64 lo = z.dir[key >> z.dir_shift];
     u64 hi = lo, step = 1;
     while (hi < z.n && z.sorted_keys[hi] < key) {  // gallop: keys[lo-1] < key stays true
@@ -405,15 +418,14 @@ struct RerankScanOp {
 __global__ void __launch_bounds__(SAB_SCAN_THREADS)
 rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
               u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ upd_idx, u32* __restrict__ upd_r,
-              u32* __restrict__ d_count, TileState<RerankScan> st, u32* __restrict__ ticket, u32 ticket_base) {
-    SAB_SHARED_VAR(u32, s_tile);
+              u32* __restrict__ d_count, TileState<RerankScan> st) {
     SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
     SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
-    const u32 tile = s_tile;
+    const u32 tile = blockIdx.x;
     const u64 base = (u64)tile * SAB_SCAN_TILE;
     const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+    const u64 edge_prev = (threadIdx.x == 0 && base > 0) ? S[base - 1] : 0ull;
+    const u64 edge_next = (threadIdx.x == SAB_SCAN_THREADS - 1 && base + SAB_SCAN_TILE < m) ? S[base + SAB_SCAN_TILE] : 0ull;
 
     u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
 #pragma unroll
@@ -435,8 +447,7 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
     u64 key[SAB_SCAN_ITEMS + 2];
 #pragma unroll
     for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
-    key[0] = (j0 > 0 && j0 - 1 < m) ? S[j0 - 1] : 0ull;
-    key[SAB_SCAN_ITEMS + 1] = (j0 + SAB_SCAN_ITEMS < m) ? S[j0 + SAB_SCAN_ITEMS] : 0ull;
+    tile_neighbor_keys(key, edge_prev, edge_next);
 
     RerankScan mine;
     mine.ogs = 0;
@@ -528,8 +539,15 @@ static inline int sab_ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
 }
 
 // Code table and key shape from the byte histogram: codes 1..sigma in byte order (0 = absent byte /
-// past the end), b = ceil(log2(sigma+1)) bits per symbol, k symbols per key.
-static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, int* b_out, int* k_out) {
+// past the end).  Keys are mixed-radix numbers in base sigma+1 (dense: no bit is wasted on unused
+// codes, so more symbols fit a radix pass and the key space is evenly filled), k symbols per key,
+// key_bits = bits needed for base^k - 1.
+//
+// Cost model, in bytes moved per suffix: P radix passes of 24 B each, plus ~SAB_ACTIVE_COST bytes over
+// all doubling rounds for every suffix still tied after the initial sort; a suffix stays tied with
+// probability ~ n * 2^-(k*H2) (H2 = order-0 collision entropy; higher-order structure only makes the
+// estimate optimistic, never the result wrong).
+static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, u32* base_out, int* k_out, int* key_bits_out) {
     u32 sigma = 0;
     double sum_p2 = 0.0;
     for (int ch = 0; ch < 256; ++ch) {
@@ -538,23 +556,40 @@ static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, 
         const double p = n ? (double)hist[ch] / (double)n : 0.0;
         sum_p2 += p * p;
     }
-    int b = sab_ceil_log2_u64((u64)sigma + 1);  // codes 0..sigma
-    if (b < 1) b = 1;
-    // symbols per key: enough collision entropy to separate n random suffixes with SAB_MARGIN_BITS to
-    // spare, rounded up to whole 8-bit radix passes; never more than fit in 64 bits
-    // Cost model, in bytes moved per suffix: P radix passes of 24 B each, plus ~SAB_ACTIVE_COST bytes over
-    // all doubling rounds for every suffix still tied after the initial sort; a suffix stays tied with
-    // probability ~ n * 2^-(k*H2) (H2 = order-0 collision entropy; higher-order structure only makes the
-    // estimate optimistic, never the result wrong).
-    const int k_full = 64 / b;
-    int k = k_full;
-    const double h2 = sum_p2 < 1.0 ? -log2(sum_p2) : 0.0;
-    if (h2 > 1e-3) {
+    const u32 base = sigma + 1 < 2 ? 2 : sigma + 1;
+    // kmax[p] = most symbols whose key fits p radix passes (and 64 bits)
+    int k_of_pass[SAB_MAX_PASSES + 1];
+    int bits_of_k[65];
+    {
+        unsigned __int128 pw = 1;
+        int kk = 0;
+        bits_of_k[0] = 0;
+        while (kk < 64) {
+            pw *= base;
+            if (pw > ((unsigned __int128)1 << 64)) break;
+            ++kk;
+            unsigned __int128 m = pw - 1;  // largest key
+            int bits = 0;
+            while (m) {
+                ++bits;
+                m >>= 1;
+            }
+            bits_of_k[kk] = bits < 1 ? 1 : bits;
+        }
+        const int k_full = kk < 1 ? 1 : kk;
+        for (int p = 1; p <= SAB_MAX_PASSES; ++p) {
+            int best = 0;
+            for (int q = 1; q <= k_full; ++q)
+                if (bits_of_k[q] <= p * SAB_RADIX_BITS) best = q;
+            k_of_pass[p] = best;
+        }
+    }
+    int k = k_of_pass[SAB_MAX_PASSES];
+    const double h2 = sum_p2 < 1.0 && sum_p2 > 0.0 ? -log2(sum_p2) : 0.0;
+    if (h2 > 1e-3 && n > 0) {
         double best = 1e300;
-        const int p_full = (k_full * b + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
-        for (int p = 1; p <= p_full; ++p) {
-            int kp = p * SAB_RADIX_BITS / b;
-            if (kp > k_full) kp = k_full;
+        for (int p = 1; p <= SAB_MAX_PASSES; ++p) {
+            const int kp = k_of_pass[p];
             if (kp < 1) continue;
             double tied = exp2(log2((double)n) - (double)kp * h2);
             if (tied > 1.0) tied = 1.0;
@@ -565,16 +600,18 @@ static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, 
             }
         }
     }
+    if (k < 1) k = 1;
     *sigma_out = sigma;
-    *b_out = b;
+    *base_out = base;
     *k_out = k;
+    *key_bits_out = bits_of_k[k];
 }
 
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
-    int dir_bits = sab_ceil_log2_u64(n) - 4;
-    if (dir_bits > 26) dir_bits = 26;
+    int dir_bits = sab_ceil_log2_u64(n) - 2;
+    if (dir_bits > 28) dir_bits = 28;
     if (dir_bits < 1) dir_bits = 1;
     return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) +
            sab_align_up((((size_t)1 << dir_bits) + 8) * 4, 256) + 4096;
@@ -623,14 +660,15 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     memcpy(h_hist, c->h_small + 64, sizeof(h_hist));
     u16 lut[256];
     u32 sigma = 0;
-    int b = 1, k = 1;
+    u32 base = 2;
+    int k = 1, key_bits = 1;
     {
         u64 h64[256];
         for (int ch = 0; ch < 256; ++ch) h64[ch] = h_hist[ch];
-        sab_plan_alphabet(h64, n, lut, &sigma, &b, &k);
+        sab_plan_alphabet(h64, n, lut, &sigma, &base, &k, &key_bits);
     }
     S.sigma = sigma;
-    S.bits_per_symbol = (u32)b;
+    S.bits_per_symbol = (u32)sab_ceil_log2_u64(base);
     S.symbols_per_key = (u32)k;
     u16* d_lut = (u16*)(c->d_counters + 16 + 256);
     memcpy(c->h_small + 384, lut, sizeof(lut));  // pinned staging: the async copy must not read the stack later
@@ -638,13 +676,12 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
 
     // 2. packed keys
     SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
-               (const u16*)d_lut, b, k, buf.k[0]);
+               (const u16*)d_lut, base, k, buf.k[0]);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     S.kernel_launches++;
 
     // 3. sort (key, i)
-    const int key_bits = k * b;
     SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, key_bits, /*iota=*/true, &S.passes[0]));
 
     // 4. ranks, SA skeleton, active list, bucket directory over the sorted keys
@@ -653,8 +690,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     const u32* sortedI = buf.v[buf.cur];
     u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
-    int dir_bits = sab_ceil_log2_u64(n) - 4;
-    if (dir_bits > 26) dir_bits = 26;
+    int dir_bits = sab_ceil_log2_u64(n) - 2;
+    if (dir_bits > 28) dir_bits = 28;
     if (dir_bits > key_bits) dir_bits = key_bits;
     if (dir_bits < 1) dir_bits = 1;
     const int dir_shift = key_bits - dir_bits;
@@ -668,10 +705,9 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
         TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
         sab_prof_begin(c, 3);
         SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, n, 1u, rank,
-                   (u32*)nullptr, d_sa + 1, r1buf, act_idx, d_m, dir, dir_shift, ts, c->d_ticket, c->ticket_host);
+                   (u32*)nullptr, d_sa + 1, r1buf, act_idx, d_m, dir, dir_shift, ts);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
-        c->ticket_host += (u32)tiles;
         S.kernel_launches++;
     }
     SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -689,7 +725,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     z.lut = d_lut;
     z.dir = dir;
     z.n = n;
-    z.b = b;
+    z.base = base;
     z.k = k;
     z.dir_shift = dir_shift;
     SortBuffers<u64> rb;  // buffers of the rounds
@@ -739,10 +775,9 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             sab_prof_begin(c, 3);
             SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)rb.k[rb.cur],
                        (const u32*)rb.v[rb.cur], m, rank, d_sa, r1buf, rb.v[rb.cur ^ 1], (u32*)nullptr, (u32*)nullptr, d_m,
-                       ts, c->d_ticket, c->ticket_host);
+                       ts);
             sab_prof_end(c);
             SAB_LAUNCH_CHECK();
-            c->ticket_host += (u32)tiles;
             S.kernel_launches++;
         }
         rb.cur ^= 1;

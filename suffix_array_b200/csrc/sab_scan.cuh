@@ -41,7 +41,7 @@ __device__ __forceinline__ T warp_reduce_pod(T v, Op op) {
 // Returns, in every thread of the block, the combination (op, commutative + associative) of the
 // aggregates of all tiles < `tile`.  `aggregate` must be valid in thread 0.  Must be called by all
 // threads of the block (it contains __syncthreads).  Tiles must be numbered in launch order (a
-// tile may only wait on tiles whose blocks have already started): use blockIdx.x with a 1-D grid.
+// tile may only wait on tiles whose blocks have already started): blockIdx.x of a 1-D grid.
 template <typename T, typename Op>
 __device__ __forceinline__ T tile_exclusive_prefix(const TileState<T>& st, u32 tile, T aggregate, Op op, T identity) {
     SAB_SHARED_VAR(T, s_prefix);

@@ -83,6 +83,13 @@ class _Ctx:
             _lib.check(rc, what)
         return rc
 
+    def call(self, name, *args):
+        """One library step.  The library runs on its own stream and synchronises it before returning;
+        torch work queued on the current stream (fills, copies, collectives) must be complete before the
+        step touches those buffers, hence the synchronise here."""
+        self.sync()
+        return self.check(getattr(self.L, name)(*args), name)
+
     def sync(self):
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
@@ -115,8 +122,8 @@ def _to_owner(cx, keys, vals, count, add, B):
     kp = cx.empty(count, torch.int32)
     vp = cx.empty(count, torch.int32)
     cnt = np.zeros(cx.P, dtype=np.uint64)
-    cx.check(cx.L.sab200_dist_partition_owner(_p(keys), _p(vals), count, add, B, cx.P, _p(kp), _p(vp),
-                                              cnt.ctypes.data_as(C.c_void_p), cx.dev), "sab200_dist_partition_owner")
+    cx.call("sab200_dist_partition_owner", _p(keys), _p(vals), count, add, B, cx.P, _p(kp), _p(vp),
+                                              cnt.ctypes.data_as(C.c_void_p), cx.dev)
     return kp, vp, [int(x) for x in cnt]
 
 
@@ -126,7 +133,7 @@ def _send_ranks(cx, idx, ranks, count, B, lo, rank_local):
     recv = cx.exchange_counts(send)
     ri = cx.all_to_all(kp, send, recv)
     rr = cx.all_to_all(vp, send, recv)
-    cx.check(cx.L.sab200_dist_scatter(_p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev), "sab200_dist_scatter")
+    cx.call("sab200_dist_scatter", _p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev)
 
 
 def dist_saca(shard, n, device, group=None, stats=None):
@@ -143,27 +150,25 @@ def dist_saca(shard, n, device, group=None, stats=None):
         raise ValueError("text longer than MAX_LENGTH")
     B, lo, hi = shard_bounds(n, rank, P)
     count = hi - lo
-    cx.check(L.sab200_dist_begin(cx.dev), "sab200_dist_begin")
+    cx.call("sab200_dist_begin", cx.dev)
     d_text = torch.as_tensor(shard, dtype=torch.uint8).to(cx.device)
     need = min(count + HALO, n - lo)
     if d_text.numel() < need:
         raise ValueError("shard too short: %d bytes, need %d (own positions + halo)" % (d_text.numel(), need))
     # 1. common alphabet / key shape
     d_hist = torch.zeros(256, dtype=torch.int64, device=cx.device)
-    cx.check(L.sab200_dist_hist(_p(d_text), count, _p(d_hist), cx.dev), "sab200_dist_hist")
+    cx.call("sab200_dist_hist", _p(d_text), count, _p(d_hist), cx.dev)
     dist.all_reduce(d_hist, group=cx.group)
     hist = d_hist.cpu().numpy().astype(np.uint64)
     lut = np.zeros(256, dtype=np.uint16)
     b, k = C.c_int32(), C.c_int32()
-    cx.check(L.sab200_dist_plan(hist.ctypes.data_as(C.c_void_p), n, lut.ctypes.data_as(C.c_void_p), C.byref(b), C.byref(k)),
-             "sab200_dist_plan")
+    cx.call("sab200_dist_plan", hist.ctypes.data_as(C.c_void_p), n, lut.ctypes.data_as(C.c_void_p), C.byref(b), C.byref(k))
     b, k = b.value, k.value
-    key_bits = b * k
+    key_bits = max(1, (b ** k - 1).bit_length())  # keys are mixed-radix numbers in base b = sigma + 1
     # 2. keys of own positions, splitters from a sample
     keys = cx.empty(count, torch.int64)
     idx = cx.empty(count, torch.int32)
-    cx.check(L.sab200_dist_pack(_p(d_text), lo, count, n, lut.ctypes.data_as(C.c_void_p), b, k, _p(keys), _p(idx), cx.dev),
-             "sab200_dist_pack")
+    cx.call("sab200_dist_pack", _p(d_text), lo, count, n, lut.ctypes.data_as(C.c_void_p), b, k, _p(keys), _p(idx), cx.dev)
     S = 2048
     sample = torch.zeros(S + 1, dtype=torch.int64, device=cx.device)
     if count:
@@ -182,8 +187,8 @@ def dist_saca(shard, n, device, group=None, stats=None):
     kp = cx.empty(count, torch.int64)
     ip = cx.empty(count, torch.int32)
     cnt = np.zeros(P, dtype=np.uint64)
-    cx.check(L.sab200_dist_partition_keys(_p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
-                                          cnt.ctypes.data_as(C.c_void_p), cx.dev), "sab200_dist_partition_keys")
+    cx.call("sab200_dist_partition_keys", _p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
+                                          cnt.ctypes.data_as(C.c_void_p), cx.dev)
     send = [int(x) for x in cnt]
     recv = cx.exchange_counts(send)
     k0 = cx.all_to_all(kp, send, recv)
@@ -193,7 +198,7 @@ def dist_saca(shard, n, device, group=None, stats=None):
     # 4. local sort: this rank's slice of the suffix array
     k1 = cx.empty(R, torch.int64)
     v1 = cx.empty(R, torch.int32)
-    which = cx.check(L.sab200_dist_sort_pairs(_p(k0), _p(k1), _p(v0), _p(v1), R, key_bits, cx.dev), "sab200_dist_sort_pairs")
+    which = cx.call("sab200_dist_sort_pairs", _p(k0), _p(k1), _p(v0), _p(v1), R, key_bits, cx.dev)
     ks, vs = (k0, v0) if which == 0 else (k1, v1)
     sizes = torch.zeros(P, dtype=torch.int64, device=cx.device)
     sizes[rank] = R
@@ -205,8 +210,8 @@ def dist_saca(shard, n, device, group=None, stats=None):
     act_r1 = cx.empty(R, torch.int32)
     act_idx = cx.empty(R, torch.int32)
     m = C.c_uint64()
-    cx.check(L.sab200_dist_init_ranks(_p(ks), _p(vs), R, sa_off, _p(sa_local), _p(rank_seq), _p(act_r1), _p(act_idx),
-                                      C.byref(m), cx.dev), "sab200_dist_init_ranks")
+    cx.call("sab200_dist_init_ranks", _p(ks), _p(vs), R, sa_off, _p(sa_local), _p(rank_seq), _p(act_r1), _p(act_idx),
+                                      C.byref(m), cx.dev)
     m = m.value
     # 5. every rank travels to the owner of its text position
     rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n (rank 0) if owned
@@ -233,27 +238,26 @@ def dist_saca(shard, n, device, group=None, stats=None):
         recv = cx.exchange_counts(send)
         q = cx.all_to_all(ipart, send, recv)
         ans = cx.empty(q.numel(), torch.int32)
-        cx.check(L.sab200_dist_gather(_p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev), "sab200_dist_gather")
+        cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev)
         r2 = cx.all_to_all(ans, recv, send)
         key64 = cx.empty(m, torch.int64)
-        cx.check(L.sab200_dist_make_keys(_p(rpart), _p(r2), m, _p(key64), cx.dev), "sab200_dist_make_keys")
+        cx.call("sab200_dist_make_keys", _p(rpart), _p(r2), m, _p(key64), cx.dev)
         key_tmp = cx.empty(m, torch.int64)
         idx_tmp = cx.empty(m, torch.int32)
-        which = cx.check(L.sab200_dist_sort_pairs(_p(key64), _p(key_tmp), _p(ipart), _p(idx_tmp), m, 32 + rank_bits, cx.dev),
-                         "sab200_dist_sort_pairs")
+        which = cx.call("sab200_dist_sort_pairs", _p(key64), _p(key_tmp), _p(ipart), _p(idx_tmp), m, 32 + rank_bits, cx.dev)
         sk, si = (key64, ipart) if which == 0 else (key_tmp, idx_tmp)
         out_r1 = cx.empty(m, torch.int32)
         out_idx = cx.empty(m, torch.int32)
         upd_idx = cx.empty(m, torch.int32)
         upd_r = cx.empty(m, torch.int32)
         kept = C.c_uint64()
-        cx.check(L.sab200_dist_rerank(_p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
-                                      C.byref(kept), cx.dev), "sab200_dist_rerank")
+        cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
+                                      C.byref(kept), cx.dev)
         _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
-    cx.check(L.sab200_dist_end(cx.dev), "sab200_dist_end")
+    cx.call("sab200_dist_end", cx.dev)
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives})
