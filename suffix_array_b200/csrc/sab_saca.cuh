@@ -29,6 +29,13 @@
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_RANK_EMPTY 0xffffffffu
 #ifdef SAB_EMU
+#ifndef SAB_FILTER_MIN
+#define SAB_FILTER_MIN ((u64)3000)
+#endif
+#else
+#define SAB_FILTER_MIN ((u64)1 << 20)
+#endif
+#ifdef SAB_EMU
 #define SAB_ACTIVE_COST 30.0  // emulator runs are tiny: keep the doubling rounds exercised
 #else
 #define SAB_ACTIVE_COST 300.0
@@ -153,7 +160,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& tot
 // Global memory is always touched with consecutive lanes on consecutive elements (full sectors); the
 // exchange to the blocked arrangement the scans need (thread t owns elements t*ITEMS .. +ITEMS-1) goes
 // through shared memory, padded by one word per 32 so both access patterns are bank-conflict free.
-#define SAB_PAD(o) ((o) + ((o) >> 5))
+#define SAB_PAD(o) ((o) + ((o) >> 5))  // NB: evaluates its argument twice
 #define SAB_TILE_WORDS (SAB_SCAN_TILE + SAB_SCAN_TILE / 32 + 8)
 
 // striped registers: element k of thread t is tile element t + k*THREADS
@@ -531,6 +538,127 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
     if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= m) *d_count = prefix.cnt + total.cnt;
 }
 
+// ------------------------------------------------------------------ 5c. skip groups that cannot split
+// On repetitive texts most groups gain no information in a round: all their members fetch the same
+// second rank.  Such a group keeps its order and its rank, so sorting it is wasted traffic.
+// mark_split_groups flags (bitmap over SA positions) the groups that hold two different second ranks;
+// split_filter compacts the records of flagged groups in place (they go on to the sort) and moves the
+// rest, untouched, straight into the next round's active list.
+__global__ void __launch_bounds__(256)
+mark_split_groups_kernel(const u64* __restrict__ key64, u64 m, u32* __restrict__ bitmap) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 || j >= m) return;
+    const u64 a = key64[j - 1], b = key64[j];
+    if ((a >> 32) == (b >> 32) && (u32)a != (u32)b) {
+        const u32 r1 = (u32)(b >> 32);
+        atomicOr(&bitmap[r1 >> 5], 1u << (r1 & 31u));
+    }
+}
+
+struct FilterScan {
+    u32 sort_cnt;
+    u32 stay_cnt;
+};
+struct FilterScanOp {
+    __device__ __forceinline__ FilterScan operator()(const FilterScan& a, const FilterScan& b) const {
+        FilterScan r;
+        r.sort_cnt = a.sort_cnt + b.sort_cnt;
+        r.stay_cnt = a.stay_cnt + b.stay_cnt;
+        return r;
+    }
+};
+
+// key64 / idx are compacted IN PLACE (a tile's output range ends before its own input and is only
+// written once every predecessor has published its aggregate, i.e. has finished reading its input).
+__global__ void __launch_bounds__(SAB_SCAN_THREADS)
+split_filter_kernel(u64* key64, u32* idx_io, u64 m, const u32* __restrict__ bitmap, u32* __restrict__ stay_r1,
+                    u32* __restrict__ stay_idx, u32* __restrict__ d_counts, TileState<FilterScan> st) {
+    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
+    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
+    const u32 tile = blockIdx.x;
+    const u64 base = (u64)tile * SAB_SCAN_TILE;
+    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
+    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
+        u64 key = 0;
+        u32 ix = 0;
+        if (j < m) {
+            key = key64[j];
+            ix = idx_io[j];
+        }
+        klo[k] = (u32)key;
+        khi[k] = (u32)(key >> 32);
+        idx[k] = ix;
+    }
+    tile_striped_to_blocked(klo, s_a);
+    tile_striped_to_blocked(khi, s_b);
+    tile_striped_to_blocked(idx, s_a);
+    FilterScan mine;
+    mine.sort_cnt = 0;
+    mine.stay_cnt = 0;
+    u32 sortbits = 0;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+        if (j0 + k < m) {
+            const u32 r1 = khi[k];
+            if ((bitmap[r1 >> 5] >> (r1 & 31u)) & 1u) {
+                sortbits |= 1u << k;
+                mine.sort_cnt++;
+            } else {
+                mine.stay_cnt++;
+            }
+        }
+    }
+    FilterScan ident;
+    ident.sort_cnt = 0;
+    ident.stay_cnt = 0;
+    FilterScan total;
+    FilterScan excl = block_exclusive_scan<FilterScan, FilterScanOp, SAB_SCAN_THREADS>(mine, FilterScanOp(), ident, total);
+    FilterScan prefix = tile_exclusive_prefix<FilterScan, FilterScanOp>(st, tile, total, FilterScanOp(), ident);
+    // records to sort: keys (two words) ...
+    u32 local = excl.sort_cnt;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
+        if ((j0 + k < m) && (sortbits & (1u << k))) {
+            s_a[SAB_PAD(local)] = klo[k];
+            s_b[SAB_PAD(local)] = khi[k];
+            ++local;
+        }
+    __syncthreads();
+    for (u32 o = threadIdx.x; o < total.sort_cnt; o += SAB_SCAN_THREADS)
+        key64[prefix.sort_cnt + o] = ((u64)s_b[SAB_PAD(o)] << 32) | s_a[SAB_PAD(o)];
+    __syncthreads();
+    // ... and their suffix indices
+    local = excl.sort_cnt;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
+        if ((j0 + k < m) && (sortbits & (1u << k))) {
+            s_a[SAB_PAD(local)] = idx[k];
+            ++local;
+        }
+    __syncthreads();
+    tile_flush_compact(idx_io, prefix.sort_cnt, total.sort_cnt, s_a);
+    __syncthreads();
+    // records that stay as they are
+    local = excl.stay_cnt;
+#pragma unroll
+    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
+        if ((j0 + k < m) && !(sortbits & (1u << k))) {
+            s_a[SAB_PAD(local)] = khi[k];
+            s_b[SAB_PAD(local)] = idx[k];
+            ++local;
+        }
+    __syncthreads();
+    tile_flush_compact(stay_r1, prefix.stay_cnt, total.stay_cnt, s_a);
+    tile_flush_compact(stay_idx, prefix.stay_cnt, total.stay_cnt, s_b);
+    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= m) {
+        d_counts[0] = prefix.sort_cnt + total.sort_cnt;
+        d_counts[1] = prefix.stay_cnt + total.stay_cnt;
+    }
+}
+
 // ------------------------------------------------------------------ driver (device pointers)
 static inline int sab_ceil_log2_u64(u64 x) {  // smallest b with 2^b >= x
     int b = 0;
@@ -614,7 +742,7 @@ static inline size_t sab_saca_workspace_bytes(u64 n) {
     if (dir_bits > 28) dir_bits = 28;
     if (dir_bits < 1) dir_bits = 1;
     return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) +
-           sab_align_up((((size_t)1 << dir_bits) + 8) * 4, 256) + 4096;
+           sab_align_up((((size_t)1 << dir_bits) + 8) * 4, 256) + sab_align_up((N / 32 + 8) * 4, 256) + 4096;
 }
 
 
@@ -696,6 +824,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     if (dir_bits < 1) dir_bits = 1;
     const int dir_shift = key_bits - dir_bits;
     u32* dir = sab_arena_take<u32>(c, ((size_t)1 << dir_bits) + 8);
+    u32* split_bitmap = sab_arena_take<u32>(c, (size_t)n / 32 + 8);
     SAB_CUDA_TRY(cudaMemsetAsync(rank, 0xff, n * sizeof(u32), st));
     SAB_CUDA_TRY(cudaMemsetAsync(rank + n, 0, sizeof(u32), st));  // the empty suffix has rank 0
     c->h_small[32] = (u32)n;
@@ -755,6 +884,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     u64 h = (u64)k;
     u32 round = 0;
     const int rank_bits = sab_ceil_log2_u64(n + 2);
+    // the split filter (5c) pays off while few groups split: repetitive texts, early rounds
+    bool filter_on = (z.sorted_keys == nullptr) && m >= SAB_FILTER_MIN;
     while (m > 0) {
         ++round;
         if (round >= SAB_MAX_ROUNDS || h > n) {
@@ -768,22 +899,56 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         S.kernel_launches++;
-        SAB_TRY(sab_radix_sort<u64>(c, rb, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
-        {
+        u64 n_sort = m, n_stay = 0;
+        if (filter_on && m >= SAB_FILTER_MIN) {
             const u64 tiles = div_up64(m, SAB_SCAN_TILE);
-            TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
+            TileState<FilterScan> ts = sab_tile_state<FilterScan>(c, tiles);
             sab_prof_begin(c, 3);
-            SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)rb.k[rb.cur],
-                       (const u32*)rb.v[rb.cur], m, rank, d_sa, r1buf, rb.v[rb.cur ^ 1], (u32*)nullptr, (u32*)nullptr, d_m,
-                       ts);
+            SAB_CUDA_TRY(cudaMemsetAsync(split_bitmap, 0, ((size_t)n / 32 + 8) * sizeof(u32), st));
+            SAB_LAUNCH(mark_split_groups_kernel, (unsigned)div_up64(m, 256), 256, 0, st, (const u64*)rb.k[rb.cur], m, split_bitmap);
+            SAB_LAUNCH_CHECK();
+            SAB_LAUNCH(split_filter_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, rb.k[rb.cur], rb.v[rb.cur], m,
+                       (const u32*)split_bitmap, r1buf, rb.v[rb.cur ^ 1], d_m + 2, ts);
             sab_prof_end(c);
             SAB_LAUNCH_CHECK();
-            S.kernel_launches++;
+            S.kernel_launches += 2;
+            SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SAB_CUDA_TRY(cudaStreamSynchronize(st));
+            n_sort = c->h_small[0];
+            n_stay = c->h_small[1];
+            if (n_sort * 10 > m * 7) filter_on = false;  // from here on most groups split every round
+        }
+        u64 kept = 0;
+        if (n_sort > 0) {
+            // sort the n_sort records at the front of (k[cur], v[cur]); the spare payload buffer starts
+            // behind the n_stay records already parked in v[cur^1]
+            SortBuffers<u64> sb;
+            sb.k[0] = rb.k[rb.cur];
+            sb.k[1] = rb.k[rb.cur ^ 1];
+            sb.v[0] = rb.v[rb.cur];
+            sb.v[1] = rb.v[rb.cur ^ 1] + n_stay;
+            sb.cur = 0;
+            SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+            u32* out_idx = (sb.cur == 0) ? rb.v[rb.cur ^ 1] + n_stay : rb.v[rb.cur];
+            {
+                const u64 tiles = div_up64(n_sort, SAB_SCAN_TILE);
+                TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
+                sab_prof_begin(c, 3);
+                SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)sb.k[sb.cur],
+                           (const u32*)sb.v[sb.cur], n_sort, rank, d_sa, r1buf + n_stay, out_idx, (u32*)nullptr, (u32*)nullptr,
+                           d_m, ts);
+                sab_prof_end(c);
+                SAB_LAUNCH_CHECK();
+                S.kernel_launches++;
+            }
+            SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            SAB_CUDA_TRY(cudaStreamSynchronize(st));
+            kept = c->h_small[0];
+            if (sb.cur != 0 && kept > 0)  // the survivors were written to the other buffer: append them to the parked ones
+                SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1] + n_stay, rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
         }
         rb.cur ^= 1;
-        SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        SAB_CUDA_TRY(cudaStreamSynchronize(st));
-        m = c->h_small[0];
+        m = n_stay + kept;
         S.active[round] = m;
         h *= 2;
     }
