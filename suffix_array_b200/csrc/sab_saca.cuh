@@ -28,6 +28,7 @@
 #define SAB_SCAN_ITEMS 8
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_RANK_EMPTY 0xffffffffu
+#define SAB_PAD(o) ((o) + ((o) >> 5))  // shared-memory padding, one word per 32; NB: evaluates its argument twice
 #ifdef SAB_EMU
 #ifndef SAB_FILTER_MIN
 #define SAB_FILTER_MIN ((u64)3000)
@@ -70,6 +71,12 @@ __global__ void __launch_bounds__(256) alphabet_hist_kernel(const u8* __restrict
     if (c) atomicAdd(&hist[threadIdx.x], c);
 }
 
+static inline u64 sab_pow_u64(u64 b, int e) {
+    u64 r = 1;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+}
+
 // ------------------------------------------------------------------ 2. packed initial keys
 #define SAB_PACK_THREADS 256
 #define SAB_PACK_ITEMS 8
@@ -86,13 +93,18 @@ __device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, c
     return key;
 }
 
-// lut[c] = code of byte c (1..sigma); key = sum code_t * base^(k-1-t), base = sigma + 1.  Keys are produced for positions
-// [0, count); positions >= n are past the end of the text (count < n when the buffer is a shard + halo).
+// lut[c] = code of byte c (1..sigma); key = sum code_t * radix^(k-1-t), radix = sigma + 1, top = radix^(k-1).
+// Keys are produced for positions [0, count); positions >= n are past the end of the text (count < n
+// when the buffer is a shard + halo).  Each thread owns SAB_PACK_ITEMS consecutive positions: the first
+// key costs k multiply-adds, each next one slides the window (drop the leading symbol, append one);
+// the keys leave through shared memory so that global stores are coalesced.
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
-pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k,
+pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k, u64 top,
                  u64* __restrict__ keys) {
     SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
+    SAB_SHARED_ARRAY(u32, s_lo, SAB_PACK_TILE + SAB_PACK_TILE / 32 + 8);
+    SAB_SHARED_ARRAY(u32, s_hi, SAB_PACK_TILE + SAB_PACK_TILE / 32 + 8);
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
     const u64 tile0 = (u64)blockIdx.x * SAB_PACK_TILE;
@@ -101,15 +113,21 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
         s_code[o] = i < n ? s_lut[text[i]] : (u16)0;
     }
     __syncthreads();
+    const int o0 = threadIdx.x * SAB_PACK_ITEMS;
+    u64 key = 0;
+    for (int t = 0; t < k; ++t) key = key * radix + (u64)s_code[o0 + t];
+#pragma unroll
+    for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
+        s_lo[SAB_PAD(o0 + j)] = (u32)key;
+        s_hi[SAB_PAD(o0 + j)] = (u32)(key >> 32);
+        key = (key - (u64)s_code[o0 + j] * top) * radix + (u64)s_code[o0 + j + k];
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
         const int o = threadIdx.x + j * SAB_PACK_THREADS;
         const u64 i = tile0 + o;
-        if (i < count) {
-            u64 key = 0;
-            for (int t = 0; t < k; ++t) key = key * radix + (u64)s_code[o + t];
-            keys[i] = key;
-        }
+        if (i < count) keys[i] = ((u64)s_hi[SAB_PAD(o)] << 32) | s_lo[SAB_PAD(o)];
     }
 }
 
@@ -160,7 +178,6 @@ __device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& tot
 // Global memory is always touched with consecutive lanes on consecutive elements (full sectors); the
 // exchange to the blocked arrangement the scans need (thread t owns elements t*ITEMS .. +ITEMS-1) goes
 // through shared memory, padded by one word per 32 so both access patterns are bank-conflict free.
-#define SAB_PAD(o) ((o) + ((o) >> 5))  // NB: evaluates its argument twice
 #define SAB_TILE_WORDS (SAB_SCAN_TILE + SAB_SCAN_TILE / 32 + 8)
 
 // striped registers: element k of thread t is tile element t + k*THREADS
@@ -804,7 +821,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
 
     // 2. packed keys
     SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
-               (const u16*)d_lut, base, k, buf.k[0]);
+               (const u16*)d_lut, base, k, sab_pow_u64(base, k - 1), buf.k[0]);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     S.kernel_launches++;
