@@ -77,6 +77,17 @@ class _Ctx:
         self.P = dist.get_world_size(group)
         self.a2a_bytes = 0
         self.collectives = 0
+        self.phase_ms = {}
+        self._t = None
+
+    def mark(self, name):
+        """Phase timer (host clock around synchronised steps): time since the previous mark goes to `name`."""
+        import time
+        self.sync()
+        now = time.perf_counter()
+        if self._t is not None:
+            self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (now - self._t) * 1e3
+        self._t = now
 
     def check(self, rc, what):
         if rc < 0:
@@ -151,10 +162,12 @@ def dist_saca(shard, n, device, group=None, stats=None):
     B, lo, hi = shard_bounds(n, rank, P)
     count = hi - lo
     cx.call("sab200_dist_begin", cx.dev)
+    cx.mark("start")
     d_text = torch.as_tensor(shard, dtype=torch.uint8).to(cx.device)
     need = min(count + HALO, n - lo)
     if d_text.numel() < need:
         raise ValueError("shard too short: %d bytes, need %d (own positions + halo)" % (d_text.numel(), need))
+    cx.mark("upload")
     # 1. common alphabet / key shape
     d_hist = torch.zeros(256, dtype=torch.int64, device=cx.device)
     cx.call("sab200_dist_hist", _p(d_text), count, _p(d_hist), cx.dev)
@@ -165,6 +178,7 @@ def dist_saca(shard, n, device, group=None, stats=None):
     cx.call("sab200_dist_plan", hist.ctypes.data_as(C.c_void_p), n, lut.ctypes.data_as(C.c_void_p), C.byref(b), C.byref(k))
     b, k = b.value, k.value
     key_bits = max(1, (b ** k - 1).bit_length())  # keys are mixed-radix numbers in base b = sigma + 1
+    cx.mark("alphabet")
     # 2. keys of own positions, splitters from a sample
     keys = cx.empty(count, torch.int64)
     idx = cx.empty(count, torch.int32)
@@ -183,23 +197,27 @@ def dist_saca(shard, n, device, group=None, stats=None):
     splitters = np.zeros(max(P - 1, 1), dtype=np.uint64)
     for i in range(P - 1):
         splitters[i] = pool[min(pool.size - 1, (i + 1) * pool.size // P)] if pool.size else 0
+    cx.mark("pack+splitters")
     # 3. partition by destination, exchange
     kp = cx.empty(count, torch.int64)
     ip = cx.empty(count, torch.int32)
     cnt = np.zeros(P, dtype=np.uint64)
     cx.call("sab200_dist_partition_keys", _p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
                                           cnt.ctypes.data_as(C.c_void_p), cx.dev)
+    cx.mark("partition_keys")
     send = [int(x) for x in cnt]
     recv = cx.exchange_counts(send)
     k0 = cx.all_to_all(kp, send, recv)
     v0 = cx.all_to_all(ip, send, recv)
     del keys, idx, kp, ip
     R = k0.numel()
+    cx.mark("exchange_keys")
     # 4. local sort: this rank's slice of the suffix array
     k1 = cx.empty(R, torch.int64)
     v1 = cx.empty(R, torch.int32)
     which = cx.call("sab200_dist_sort_pairs", _p(k0), _p(k1), _p(v0), _p(v1), R, key_bits, cx.dev)
     ks, vs = (k0, v0) if which == 0 else (k1, v1)
+    cx.mark("local_sort")
     sizes = torch.zeros(P, dtype=torch.int64, device=cx.device)
     sizes[rank] = R
     dist.all_reduce(sizes, group=cx.group)
@@ -213,10 +231,12 @@ def dist_saca(shard, n, device, group=None, stats=None):
     cx.call("sab200_dist_init_ranks", _p(ks), _p(vs), R, sa_off, _p(sa_local), _p(rank_seq), _p(act_r1), _p(act_idx),
                                       C.byref(m), cx.dev)
     m = m.value
+    cx.mark("init_ranks")
     # 5. every rank travels to the owner of its text position
     rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n (rank 0) if owned
     _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
     del ks, vs, k0, k1, v0, v1, rank_seq
+    cx.mark("ranks_to_owners")
     # 6. doubling rounds
     rank_bits = max(1, int(n + 1).bit_length())
     cur_r1, cur_idx = act_r1[:m], act_idx[:m]
@@ -257,10 +277,12 @@ def dist_saca(shard, n, device, group=None, stats=None):
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
+    cx.mark("rounds")
     cx.call("sab200_dist_end", cx.dev)
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
-                      "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives})
+                      "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
+                      "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()}})
     return sa_local, sa_off
 
 

@@ -52,7 +52,7 @@ def main():
             good = bool(np.array_equal(full, exp))
             print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d" % (n, world, st["rounds"], good, st["all_to_all_bytes"]), flush=True)
             ok = ok and good
-    flag = torch.tensor([1 if ok else 0])
+    flag = torch.tensor([1 if ok else 0], device=device)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
