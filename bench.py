@@ -363,7 +363,7 @@ def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
                                   "doubling; NCCL all_to_all for keys, rank requests/answers and rank updates" % world,
                        "l2": "inputs larger than L2 (no flush needed)", "rounds": st["rounds"], "active": st["active"],
                        "symbols_per_key": st["symbols_per_key"], "collectives_per_step": st["collectives"],
-                       "phase_ms_rank0": st.get("phase_ms"),
+                       "phase_ms_rank0": st.get("phase_ms"), "wall_ms_rank0": st.get("wall_ms"),
                        "all_to_all_bytes_per_step": int(a2a)},
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (LSD radix pass, slowest rank)", "achieved": round(achieved, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,

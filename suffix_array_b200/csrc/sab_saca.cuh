@@ -23,10 +23,8 @@
 
 #include "sab_context.cuh"
 #include "sab_sort.cuh"
+#include "sab_scan_kernels.cuh"
 
-#define SAB_SCAN_THREADS 256
-#define SAB_SCAN_ITEMS 8
-#define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_RANK_EMPTY 0xffffffffu
 #define SAB_PAD(o) ((o) + ((o) >> 5))  // shared-memory padding, one word per 32; NB: evaluates its argument twice
 #ifdef SAB_EMU
@@ -131,207 +129,6 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
     }
 }
 
-// ------------------------------------------------------------------ block-wide exclusive scan of a POD
-template <typename T>
-__device__ __forceinline__ T shfl_up_pod(T v, int d) {
-    constexpr int W = sizeof(T) / 4;
-    union {
-        T t;
-        u32 w[W];
-    } u;
-    u.t = v;
-#pragma unroll
-    for (int i = 0; i < W; ++i) u.w[i] = __shfl_up_sync(SAB_FULL, u.w[i], d);
-    return u.t;
-}
-
-// returns the exclusive prefix of `v` over the threads of the block; `total` = block aggregate (all threads)
-template <typename T, typename Op, int THREADS>
-__device__ __forceinline__ T block_exclusive_scan(T v, Op op, T identity, T& total) {
-    constexpr int WARPS = THREADS / 32;
-    SAB_SHARED_ARRAY(T, s_wagg, WARPS);
-    const u32 lane = lane_id(), w = warp_id();
-    T incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        T o = shfl_up_pod<T>(incl, d);
-        if ((int)lane >= d) incl = op(o, incl);
-    }
-    if (lane == 31) s_wagg[w] = incl;
-    __syncthreads();
-    T wprefix = identity;
-    T tot = identity;
-#pragma unroll
-    for (int i = 0; i < WARPS; ++i) {
-        const T a = s_wagg[i];
-        if (i < (int)w) wprefix = op(wprefix, a);
-        tot = op(tot, a);
-    }
-    T excl = shfl_up_pod<T>(incl, 1);
-    if (lane == 0) excl = identity;
-    total = tot;
-    __syncthreads();  // s_wagg reusable
-    return op(wprefix, excl);
-}
-
-// ------------------------------------------------------------------ tile I/O: coalesced global <-> blocked registers
-// Global memory is always touched with consecutive lanes on consecutive elements (full sectors); the
-// exchange to the blocked arrangement the scans need (thread t owns elements t*ITEMS .. +ITEMS-1) goes
-// through shared memory, padded by one word per 32 so both access patterns are bank-conflict free.
-#define SAB_TILE_WORDS (SAB_SCAN_TILE + SAB_SCAN_TILE / 32 + 8)
-
-// striped registers: element k of thread t is tile element t + k*THREADS
-__device__ __forceinline__ void tile_striped_to_blocked(u32 (&v)[SAB_SCAN_ITEMS], u32* __restrict__ s) {
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) s[SAB_PAD(threadIdx.x + k * SAB_SCAN_THREADS)] = v[k];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) v[k] = s[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)];
-    __syncthreads();
-}
-
-// key[1..ITEMS] hold this thread's (blocked) items; fills key[0] / key[ITEMS+1] with the elements just
-// before / after them: neighbours inside the tile come from shared memory, the two elements outside the
-// tile (edge_prev for thread 0, edge_next for the last thread) were fetched with the tile's first loads.
-__device__ __forceinline__ void tile_neighbor_keys(u64 (&key)[SAB_SCAN_ITEMS + 2], u64 edge_prev, u64 edge_next) {
-    SAB_SHARED_ARRAY(u64, s_first, SAB_SCAN_THREADS);
-    SAB_SHARED_ARRAY(u64, s_last, SAB_SCAN_THREADS);
-    s_first[threadIdx.x] = key[1];
-    s_last[threadIdx.x] = key[SAB_SCAN_ITEMS];
-    __syncthreads();
-    key[0] = threadIdx.x > 0 ? s_last[threadIdx.x - 1] : edge_prev;
-    key[SAB_SCAN_ITEMS + 1] = threadIdx.x < SAB_SCAN_THREADS - 1 ? s_first[threadIdx.x + 1] : edge_next;
-    __syncthreads();
-}
-
-// writes `count` compacted words staged at s[SAB_PAD(0..count)] to g[out_base ..] with coalesced stores
-__device__ __forceinline__ void tile_flush_compact(u32* __restrict__ g, u64 out_base, u32 count, const u32* __restrict__ s) {
-    for (u32 o = threadIdx.x; o < count; o += SAB_SCAN_THREADS) g[out_base + o] = s[SAB_PAD(o)];
-}
-
-// ------------------------------------------------------------------ 4. ranks after the initial sort
-struct RankScan {
-    u32 head;  // largest index of a group head seen so far (index 0 is always a head)
-    u32 cnt;   // number of active (non-singleton) records seen so far
-};
-struct RankScanOp {
-    __device__ __forceinline__ RankScan operator()(const RankScan& a, const RankScan& b) const {
-        RankScan r;
-        r.head = a.head > b.head ? a.head : b.head;
-        r.cnt = a.cnt + b.cnt;
-        return r;
-    }
-};
-
-// K, I: records sorted by key.  The rank of record j is r = rank_base + (index of the head of j's group)
-// (rank_base = SA position of record 0: 1 on a single GPU, the slice offset on a multi-GPU rank).
-//   sa_out[j] = I[j]                                  (coalesced copy)
-//   records of groups larger than one -> (act_r1, act_idx)
-//   rank != null:     rank[I[j]] = r for those active records only (lazy ISA, see 4b)
-//   rank_seq != null: rank_seq[j] = r for every record (multi-GPU: ranks travel to the owner of I[j])
-//   dir != null:      dir[key >> dir_shift] = j at the first record of every directory bucket
-__global__ void __launch_bounds__(SAB_SCAN_THREADS)
-init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32 rank_base, u32* __restrict__ rank,
-                  u32* __restrict__ rank_seq, u32* __restrict__ sa_out, u32* __restrict__ act_r1,
-                  u32* __restrict__ act_idx, u32* __restrict__ d_count, u32* __restrict__ dir, int dir_shift,
-                  TileState<RankScan> st) {
-    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
-    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
-    const u32 tile = blockIdx.x;  // 1-D grids are dispatched in block order: predecessors have started
-    const u64 base = (u64)tile * SAB_SCAN_TILE;
-    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
-    const u64 edge_prev = (threadIdx.x == 0 && base > 0) ? K[base - 1] : 0ull;
-    const u64 edge_next = (threadIdx.x == SAB_SCAN_THREADS - 1 && base + SAB_SCAN_TILE < n) ? K[base + SAB_SCAN_TILE] : 0ull;
-
-    // ---- coalesced loads (striped), sa copy on the way, then exchange to blocked
-    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
-        u64 key = 0;
-        u32 ix = 0;
-        if (j < n) {
-            key = K[j];
-            ix = I[j];
-            sa_out[j] = ix;
-        }
-        klo[k] = (u32)key;
-        khi[k] = (u32)(key >> 32);
-        idx[k] = ix;
-    }
-    tile_striped_to_blocked(klo, s_a);
-    tile_striped_to_blocked(khi, s_b);
-    tile_striped_to_blocked(idx, s_a);
-    u64 key[SAB_SCAN_ITEMS + 2];  // key[0] = predecessor, key[ITEMS+1] = successor
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
-    tile_neighbor_keys(key, edge_prev, edge_next);
-
-    RankScan mine;
-    mine.head = 0;
-    mine.cnt = 0;
-    u32 headbits = 0, activebits = 0;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        if (j < n) {
-            const bool head = (j == 0) || key[k + 1] != key[k];
-            const bool next_head = (j + 1 >= n) || key[k + 2] != key[k + 1];
-            if (head) {
-                headbits |= 1u << k;
-                mine.head = (u32)j;
-                if (dir && (j == 0 || (key[k + 1] >> dir_shift) != (key[k] >> dir_shift))) dir[key[k + 1] >> dir_shift] = (u32)j;
-            }
-            if (!(head && next_head)) {
-                activebits |= 1u << k;
-                mine.cnt++;
-            }
-        }
-    }
-    RankScan ident;
-    ident.head = 0;
-    ident.cnt = 0;
-    RankScan total;
-    RankScan excl = block_exclusive_scan<RankScan, RankScanOp, SAB_SCAN_THREADS>(mine, RankScanOp(), ident, total);
-    RankScan prefix = tile_exclusive_prefix<RankScan, RankScanOp>(st, tile, total, RankScanOp(), ident);
-    u32 head_run = prefix.head > excl.head ? prefix.head : excl.head;
-    u32 local = excl.cnt;  // position of this thread's first active record inside the tile's compacted output
-    u32 rs[SAB_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        rs[k] = 0;
-        if (j < n) {
-            if (headbits & (1u << k)) head_run = (u32)j;
-            rs[k] = head_run + rank_base;
-            if (rank && (activebits & (1u << k))) rank[idx[k]] = rs[k];
-        }
-    }
-    if (rank_seq) {  // rank of every record, written with coalesced stores
-#pragma unroll
-        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) s_a[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = rs[k];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-            const u32 o = threadIdx.x + k * SAB_SCAN_THREADS;
-            if (base + o < n) rank_seq[base + o] = s_a[SAB_PAD(o)];
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        if ((j0 + k < n) && (activebits & (1u << k))) {
-            s_a[SAB_PAD(local)] = rs[k];
-            s_b[SAB_PAD(local)] = idx[k];
-            ++local;
-        }
-    }
-    __syncthreads();
-    tile_flush_compact(act_r1, prefix.cnt, total.cnt, s_a);
-    tile_flush_compact(act_idx, prefix.cnt, total.cnt, s_b);
-    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= n) *d_count = prefix.cnt + total.cnt;  // last tile
-}
-
 // ------------------------------------------------------------------ 4b. lazy inverse suffix array
 // Scattering all n initial ranks costs a partial-sector write per suffix (~30 G/s on B200, 35-50 ms per
 // GiB) although only i + h of the few active i are ever looked up.  So rank[] starts EMPTY except for
@@ -413,266 +210,6 @@ gather_rank2_kernel(const u32* __restrict__ act_r1, const u32* __restrict__ act_
         *(ulonglong2*)(key64 + j0 + 2) = o1;
     } else {
         for (u64 j = j0; j < m; ++j) key64[j] = ((u64)act_r1[j] << 32) | rank_at(rank, z, (u64)act_idx[j] + h);
-    }
-}
-
-// ------------------------------------------------------------------ 5b. re-rank + compaction
-struct RerankScan {
-    u32 ogs;  // index (in the active array) of the head of the old group
-    u32 nhs;  // index of the head of the new (refined) group
-    u32 cnt;  // records kept (still unsettled) so far
-};
-struct RerankScanOp {
-    __device__ __forceinline__ RerankScan operator()(const RerankScan& a, const RerankScan& b) const {
-        RerankScan r;
-        r.ogs = a.ogs > b.ogs ? a.ogs : b.ogs;
-        r.nhs = a.nhs > b.nhs ? a.nhs : b.nhs;
-        r.cnt = a.cnt + b.cnt;
-        return r;
-    }
-};
-
-// S, I: active records sorted by (r1, r2) (S = r1<<32 | r2).  For record j:
-//   new_r1 = r1 + (head index of its new group - head index of its old group)
-//   changed rank  -> rank[I[j]] = new_r1            (rank != null: single GPU)
-//                    upd_idx[j] = I[j], upd_r[j] = new_r1, or upd_idx[j] = 0xFFFFFFFF when unchanged
-//                    (upd_idx != null: multi-GPU, the owner of rank[I[j]] is another GPU)
-//   singleton     -> sa[new_r1] = I[j] (final), dropped
-//   otherwise     -> appended to (out_r1, out_idx)
-__global__ void __launch_bounds__(SAB_SCAN_THREADS)
-rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
-              u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ upd_idx, u32* __restrict__ upd_r,
-              u32* __restrict__ d_count, TileState<RerankScan> st) {
-    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
-    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
-    const u32 tile = blockIdx.x;
-    const u64 base = (u64)tile * SAB_SCAN_TILE;
-    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
-    const u64 edge_prev = (threadIdx.x == 0 && base > 0) ? S[base - 1] : 0ull;
-    const u64 edge_next = (threadIdx.x == SAB_SCAN_THREADS - 1 && base + SAB_SCAN_TILE < m) ? S[base + SAB_SCAN_TILE] : 0ull;
-
-    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
-        u64 key = 0;
-        u32 ix = 0;
-        if (j < m) {
-            key = S[j];
-            ix = I[j];
-        }
-        klo[k] = (u32)key;
-        khi[k] = (u32)(key >> 32);
-        idx[k] = ix;
-    }
-    tile_striped_to_blocked(klo, s_a);
-    tile_striped_to_blocked(khi, s_b);
-    tile_striped_to_blocked(idx, s_a);
-    u64 key[SAB_SCAN_ITEMS + 2];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) key[k + 1] = ((u64)khi[k] << 32) | klo[k];
-    tile_neighbor_keys(key, edge_prev, edge_next);
-
-    RerankScan mine;
-    mine.ogs = 0;
-    mine.nhs = 0;
-    mine.cnt = 0;
-    u32 oldbits = 0, newbits = 0, keepbits = 0;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        if (j < m) {
-            const bool oldhead = (j == 0) || (u32)(key[k + 1] >> 32) != (u32)(key[k] >> 32);
-            const bool newhead = (j == 0) || key[k + 1] != key[k];
-            const bool next_newhead = (j + 1 >= m) || key[k + 2] != key[k + 1];
-            if (oldhead) {
-                oldbits |= 1u << k;
-                mine.ogs = (u32)j;
-            }
-            if (newhead) {
-                newbits |= 1u << k;
-                mine.nhs = (u32)j;
-            }
-            if (!(newhead && next_newhead)) {
-                keepbits |= 1u << k;
-                mine.cnt++;
-            }
-        }
-    }
-    RerankScan ident;
-    ident.ogs = 0;
-    ident.nhs = 0;
-    ident.cnt = 0;
-    RerankScan total;
-    RerankScan excl = block_exclusive_scan<RerankScan, RerankScanOp, SAB_SCAN_THREADS>(mine, RerankScanOp(), ident, total);
-    RerankScan prefix = tile_exclusive_prefix<RerankScan, RerankScanOp>(st, tile, total, RerankScanOp(), ident);
-    RerankScan run = RerankScanOp()(prefix, excl);
-    u32 local = excl.cnt;
-    u32 nrs[SAB_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = j0 + k;
-        nrs[k] = 0;
-        if (j < m) {
-            if (oldbits & (1u << k)) run.ogs = (u32)j;
-            if (newbits & (1u << k)) run.nhs = (u32)j;
-            const u32 r1 = (u32)(key[k + 1] >> 32);
-            const u32 nr = r1 + (run.nhs - run.ogs);
-            nrs[k] = nr;
-            if (rank && nr != r1) rank[idx[k]] = nr;
-            if (!(keepbits & (1u << k))) sa[nr] = idx[k];
-        }
-    }
-    if (upd_idx) {  // dense update list, written with coalesced stores
-#pragma unroll
-        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-            const bool changed = (j0 + k < m) && nrs[k] != (u32)(key[k + 1] >> 32);
-            s_a[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = changed ? idx[k] : 0xffffffffu;
-            s_b[SAB_PAD(threadIdx.x * SAB_SCAN_ITEMS + k)] = nrs[k];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-            const u32 o = threadIdx.x + k * SAB_SCAN_THREADS;
-            if (base + o < m) {
-                upd_idx[base + o] = s_a[SAB_PAD(o)];
-                upd_r[base + o] = s_b[SAB_PAD(o)];
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        if ((j0 + k < m) && (keepbits & (1u << k))) {
-            s_a[SAB_PAD(local)] = nrs[k];
-            s_b[SAB_PAD(local)] = idx[k];
-            ++local;
-        }
-    }
-    __syncthreads();
-    tile_flush_compact(out_r1, prefix.cnt, total.cnt, s_a);
-    tile_flush_compact(out_idx, prefix.cnt, total.cnt, s_b);
-    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= m) *d_count = prefix.cnt + total.cnt;
-}
-
-// ------------------------------------------------------------------ 5c. skip groups that cannot split
-// On repetitive texts most groups gain no information in a round: all their members fetch the same
-// second rank.  Such a group keeps its order and its rank, so sorting it is wasted traffic.
-// mark_split_groups flags (bitmap over SA positions) the groups that hold two different second ranks;
-// split_filter compacts the records of flagged groups in place (they go on to the sort) and moves the
-// rest, untouched, straight into the next round's active list.
-__global__ void __launch_bounds__(256)
-mark_split_groups_kernel(const u64* __restrict__ key64, u64 m, u32* __restrict__ bitmap) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0 || j >= m) return;
-    const u64 a = key64[j - 1], b = key64[j];
-    if ((a >> 32) == (b >> 32) && (u32)a != (u32)b) {
-        const u32 r1 = (u32)(b >> 32);
-        atomicOr(&bitmap[r1 >> 5], 1u << (r1 & 31u));
-    }
-}
-
-struct FilterScan {
-    u32 sort_cnt;
-    u32 stay_cnt;
-};
-struct FilterScanOp {
-    __device__ __forceinline__ FilterScan operator()(const FilterScan& a, const FilterScan& b) const {
-        FilterScan r;
-        r.sort_cnt = a.sort_cnt + b.sort_cnt;
-        r.stay_cnt = a.stay_cnt + b.stay_cnt;
-        return r;
-    }
-};
-
-// key64 / idx are compacted IN PLACE (a tile's output range ends before its own input and is only
-// written once every predecessor has published its aggregate, i.e. has finished reading its input).
-__global__ void __launch_bounds__(SAB_SCAN_THREADS)
-split_filter_kernel(u64* key64, u32* idx_io, u64 m, const u32* __restrict__ bitmap, u32* __restrict__ stay_r1,
-                    u32* __restrict__ stay_idx, u32* __restrict__ d_counts, TileState<FilterScan> st) {
-    SAB_SHARED_ARRAY(u32, s_a, SAB_TILE_WORDS);
-    SAB_SHARED_ARRAY(u32, s_b, SAB_TILE_WORDS);
-    const u32 tile = blockIdx.x;
-    const u64 base = (u64)tile * SAB_SCAN_TILE;
-    const u64 j0 = base + (u64)threadIdx.x * SAB_SCAN_ITEMS;
-    u32 klo[SAB_SCAN_ITEMS], khi[SAB_SCAN_ITEMS], idx[SAB_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = base + threadIdx.x + (u64)k * SAB_SCAN_THREADS;
-        u64 key = 0;
-        u32 ix = 0;
-        if (j < m) {
-            key = key64[j];
-            ix = idx_io[j];
-        }
-        klo[k] = (u32)key;
-        khi[k] = (u32)(key >> 32);
-        idx[k] = ix;
-    }
-    tile_striped_to_blocked(klo, s_a);
-    tile_striped_to_blocked(khi, s_b);
-    tile_striped_to_blocked(idx, s_a);
-    FilterScan mine;
-    mine.sort_cnt = 0;
-    mine.stay_cnt = 0;
-    u32 sortbits = 0;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        if (j0 + k < m) {
-            const u32 r1 = khi[k];
-            if ((bitmap[r1 >> 5] >> (r1 & 31u)) & 1u) {
-                sortbits |= 1u << k;
-                mine.sort_cnt++;
-            } else {
-                mine.stay_cnt++;
-            }
-        }
-    }
-    FilterScan ident;
-    ident.sort_cnt = 0;
-    ident.stay_cnt = 0;
-    FilterScan total;
-    FilterScan excl = block_exclusive_scan<FilterScan, FilterScanOp, SAB_SCAN_THREADS>(mine, FilterScanOp(), ident, total);
-    FilterScan prefix = tile_exclusive_prefix<FilterScan, FilterScanOp>(st, tile, total, FilterScanOp(), ident);
-    // records to sort: keys (two words) ...
-    u32 local = excl.sort_cnt;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
-        if ((j0 + k < m) && (sortbits & (1u << k))) {
-            s_a[SAB_PAD(local)] = klo[k];
-            s_b[SAB_PAD(local)] = khi[k];
-            ++local;
-        }
-    __syncthreads();
-    for (u32 o = threadIdx.x; o < total.sort_cnt; o += SAB_SCAN_THREADS)
-        key64[prefix.sort_cnt + o] = ((u64)s_b[SAB_PAD(o)] << 32) | s_a[SAB_PAD(o)];
-    __syncthreads();
-    // ... and their suffix indices
-    local = excl.sort_cnt;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
-        if ((j0 + k < m) && (sortbits & (1u << k))) {
-            s_a[SAB_PAD(local)] = idx[k];
-            ++local;
-        }
-    __syncthreads();
-    tile_flush_compact(idx_io, prefix.sort_cnt, total.sort_cnt, s_a);
-    __syncthreads();
-    // records that stay as they are
-    local = excl.stay_cnt;
-#pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k)
-        if ((j0 + k < m) && !(sortbits & (1u << k))) {
-            s_a[SAB_PAD(local)] = khi[k];
-            s_b[SAB_PAD(local)] = idx[k];
-            ++local;
-        }
-    __syncthreads();
-    tile_flush_compact(stay_r1, prefix.stay_cnt, total.stay_cnt, s_a);
-    tile_flush_compact(stay_idx, prefix.stay_cnt, total.stay_cnt, s_b);
-    if (threadIdx.x == 0 && base + SAB_SCAN_TILE >= m) {
-        d_counts[0] = prefix.sort_cnt + total.sort_cnt;
-        d_counts[1] = prefix.stay_cnt + total.stay_cnt;
     }
 }
 

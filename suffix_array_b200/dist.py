@@ -155,6 +155,8 @@ def dist_saca(shard, n, device, group=None, stats=None):
     Returns (sa_local, sa_off): this rank's slice of the suffix array -- int32 tensor holding u32
     suffix indices for SA positions [sa_off, sa_off + len) -- the sentinel entry sa[0] = n is implied
     (rank 0's slice starts at position 1)."""
+    import time
+    t_enter = time.perf_counter()
     cx = _Ctx(device, group)
     L, P, rank = cx.L, cx.P, cx.rank
     if n > _lib.MAX_LENGTH:
@@ -282,7 +284,8 @@ def dist_saca(shard, n, device, group=None, stats=None):
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
-                      "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()}})
+                      "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()},
+                      "wall_ms": round((time.perf_counter() - t_enter) * 1e3, 2)})
     return sa_local, sa_off
 
 
