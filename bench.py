@@ -312,7 +312,8 @@ def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
     for _ in range(args.warmup):
         sdist.dist_saca(d_shard, n, dev, stats=st)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per box: eight of them would perturb the timed region
+        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pass_ms = pass_bytes = launches = pass_launches = 0
@@ -340,7 +341,8 @@ def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     slices = sum_over_ranks(st["slice"])
     assert int(slices) == n, "slices do not cover the suffix array"
     a2a = sum_over_ranks(st["all_to_all_bytes"])

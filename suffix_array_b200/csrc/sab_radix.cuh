@@ -136,7 +136,7 @@ struct OnesweepCfg {
     static constexpr size_t KEY_BYTES = (size_t)TILE * sizeof(KeyT);
     static constexpr size_t VAL_BYTES = HAS_VAL ? (size_t)TILE * sizeof(u32) : 0;
     static constexpr size_t WHIST_BYTES = (size_t)WARPS * SAB_RADIX_BINS * sizeof(u32);
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * 2 * sizeof(u32);
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * sizeof(u32);
 };
 
 // Digit extractors.  The padding key of a partial tile (all ones) must map to the last bin in use.
@@ -179,7 +179,6 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     u32* s_vals = (u32*)(smem + Cfg::KEY_BYTES);
     u32* s_goff = (u32*)(smem + Cfg::KEY_BYTES + Cfg::VAL_BYTES);          // [256] global record index - local start (mod 2^32)
     u32* s_whist = s_goff + SAB_RADIX_BINS;                                  // [WARPS][256]
-    u32* s_binstart = s_whist + WARPS * SAB_RADIX_BINS;                     // [256]
     SAB_SHARED_VAR(u32, s_tile);
     SAB_SHARED_ARRAY(u32, s_wsum, 8);
 
@@ -263,7 +262,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             u32 woff = 0;
             for (u32 i = 0; i < w; ++i) woff += s_wsum[i];
             my_start = woff + incl - my_count;
-            s_binstart[tid] = my_start;
+            // fold the bin start into the per-warp offsets: one table lookup per record in the scatter
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ++ww) s_whist[ww * SAB_RADIX_BINS + tid] += my_start;
         }
     }
     // ---- decoupled look-back, one lane per bin
@@ -293,7 +294,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 d = dop(keys[k]);
-        const u32 pos = s_binstart[d] + s_whist[w * SAB_RADIX_BINS + d] + ranks[k];
+        const u32 pos = s_whist[w * SAB_RADIX_BINS + d] + ranks[k];
         s_keys[pos] = keys[k];
         if (HAS_VAL) s_vals[pos] = vals[k];
     }
