@@ -292,7 +292,7 @@ static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, 
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
-    int dir_bits = sab_ceil_log2_u64(n) - 2;
+    int dir_bits = sab_ceil_log2_u64(n) - 4;
     if (dir_bits > 28) dir_bits = 28;
     if (dir_bits < 1) dir_bits = 1;
     return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) +
@@ -372,7 +372,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     const u32* sortedI = buf.v[buf.cur];
     u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
-    int dir_bits = sab_ceil_log2_u64(n) - 2;
+    int dir_bits = sab_ceil_log2_u64(n) - 4;
     if (dir_bits > 28) dir_bits = 28;
     if (dir_bits > key_bits) dir_bits = key_bits;
     if (dir_bits < 1) dir_bits = 1;

@@ -13,7 +13,7 @@
 
 #define SAB_SCAN_THREADS 256
 #ifndef SAB_SCAN_ITEMS
-#define SAB_SCAN_ITEMS 8
+#define SAB_SCAN_ITEMS 16
 #endif
 #define SAB_SCAN_WARPS (SAB_SCAN_THREADS / 32)
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
@@ -177,7 +177,7 @@ struct RerankScanOp {
 //                    (upd_idx != null: multi-GPU, the owner of rank[I[j]] is another GPU)
 //   singleton     -> sa[new_r1] = I[j] (final), dropped
 //   otherwise     -> appended to (out_r1, out_idx)
-__global__ void __launch_bounds__(SAB_SCAN_THREADS, 3)
+__global__ void __launch_bounds__(SAB_SCAN_THREADS, 2)
 rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
               u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ upd_idx, u32* __restrict__ upd_r,
               u32* __restrict__ d_count, TileState<RerankScan> st) {
