@@ -64,7 +64,8 @@ typedef struct sab200_stats {
  * (src/sa.rs:25,32): fills all n+1 entries of `sa`, sa[0] = n (src/saca.rs:13), sa[1..] = the
  * suffix starts in increasing suffix order (what cdivsufsort::sort_in_place wrote, src/saca.rs:14).
  * `s` (n bytes) and `sa` (n+1 entries) are HOST buffers owned by the caller (src/sa.rs:24).
- * ngpus: 1 (other values are accepted only when the multi-GPU path is built).
+ * ngpus must be 1: multi-GPU construction runs one process per GPU through sab200_dist.h (driver:
+ * suffix_array_b200/dist.py); other values return SAB200_ERR_ARGS.
  * The reference panics when n > MAX_LENGTH (src/saca.rs:10); this returns SAB200_ERR_ARGS. */
 int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus);
 

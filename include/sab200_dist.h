@@ -78,6 +78,17 @@ int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint6
                            uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
                            uint32_t* d_upd_r, uint64_t* n_kept, int32_t device);
 
+/* Peer-to-peer form of the round exchanges (NVLink): peer_rank_ptrs (host array of P device addresses)
+ * are the rank[] blocks of all GPUs mapped into this process (symmetric memory; block g holds the ranks
+ * of text positions [g*B, (g+1)*B), the last block also position n).
+ *   gather:  d_key64[t] = (d_r1[t] << 32) | rank[d_idx[t] + h], loaded from the owner GPU
+ *   scatter: rank[d_idx[t]] = d_val[t] stored into the owner GPU (d_idx[t] == 0xFFFFFFFF: skip)
+ * The caller orders the phases across ranks (nobody writes while anyone still reads). */
+int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint64_t m, uint32_t h, uint32_t B, int32_t P,
+                               const uint64_t* peer_rank_ptrs, uint64_t* d_key64, int32_t device);
+int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
+                                const uint64_t* peer_rank_ptrs, int32_t device);
+
 /* Bracket one construction on this rank: begin() clears the counters of sab200_get_stats() (and arms
  * per-launch event timing when sab200_set_profiling(1)); end() publishes them. */
 int32_t sab200_dist_begin(int32_t device);

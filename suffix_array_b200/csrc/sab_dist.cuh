@@ -286,3 +286,81 @@ extern "C" int32_t sab200_dist_end(int32_t device) {
     g_last_stats = c->stats;
     return SAB_OK;
 }
+
+// ------------------------------------------------------------------ peer-to-peer rank array (NVLink)
+// With the per-rank blocks of rank[] mapped into every process (symmetric memory), a round needs no
+// exchange step at all: the gather kernel loads rank[i+h] straight from the owner GPU over NVLink and
+// the changed ranks are stored straight into the owner's block.  The host only orders the phases
+// (every rank has finished reading before anyone writes, and vice versa).
+struct PeerTable {
+    u32* p[SAB_MAX_RANKS];
+};
+
+// key64[t] = (r1[t] << 32) | rank[idx[t] + h], rank[] block-distributed with width B over pmax+1 GPUs
+__global__ void __launch_bounds__(256)
+dist_gather_p2p_kernel(const u32* __restrict__ r1, const u32* __restrict__ idx, u64 m, u32 h, u32 B, u32 pmax, PeerTable pt,
+                       u64* __restrict__ key64) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const u64 q = (u64)idx[t] + h;
+    u32 o = (u32)(q / B);
+    if (o > pmax) o = pmax;
+    const u32 r2 = pt.p[o][q - (u64)o * B];
+    key64[t] = ((u64)r1[t] << 32) | r2;
+}
+
+// rank[idx[t]] = val[t] on the owner of idx[t]; idx == 0xFFFFFFFF marks "nothing to write"
+__global__ void __launch_bounds__(256)
+dist_scatter_p2p_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 count, u32 B, u32 pmax, PeerTable pt) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const u32 i = idx[t];
+    if (i == 0xffffffffu) return;
+    u32 o = i / B;
+    if (o > pmax) o = pmax;
+    pt.p[o][i - o * B] = val[t];
+}
+
+static int sab_peer_table(const uint64_t* peer_ptrs, int32_t P, PeerTable* pt) {
+    if (!peer_ptrs || P < 1 || P > SAB_MAX_RANKS) return SAB_ERR_ARGS;
+    for (int i = 0; i < SAB_MAX_RANKS; ++i) pt->p[i] = i < P ? (u32*)(uintptr_t)peer_ptrs[i] : nullptr;
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint64_t m, uint32_t h, uint32_t B,
+                                          int32_t P, const uint64_t* peer_rank_ptrs, uint64_t* d_key64, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    PeerTable pt;
+    SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
+    if (B == 0) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (m) {
+        sab_prof_begin(c, 4);
+        SAB_LAUNCH(dist_gather_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, c->stream, d_r1, d_idx, m, h, B, (u32)P - 1, pt, d_key64);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        c->stats.kernel_launches++;
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
+                                           const uint64_t* peer_rank_ptrs, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    PeerTable pt;
+    SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
+    if (B == 0) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (count) {
+        sab_prof_begin(c, 3);
+        SAB_LAUNCH(dist_scatter_p2p_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_idx, d_val, count, B, (u32)P - 1, pt);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        c->stats.kernel_launches++;
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}

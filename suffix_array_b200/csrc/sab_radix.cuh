@@ -113,6 +113,14 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
 #ifndef SAB_HW_MATCH_EVERY
 #define SAB_HW_MATCH_EVERY 0
 #endif
+// SAB_MATCH_SMEM = 1: peers through a per-warp shared-memory mask table (atomicOr, read back, leader
+// clears) instead of the eight ballots
+#ifndef SAB_MATCH_SMEM
+#define SAB_MATCH_SMEM 0
+#endif
+#ifndef SAB_LB_DEPTH
+#define SAB_LB_DEPTH 8
+#endif
 __device__ __forceinline__ u32 match_digit(u32 d) {
 #if SAB_MATCH_HW
     return __match_any_sync(SAB_FULL, d);
@@ -136,7 +144,8 @@ struct OnesweepCfg {
     static constexpr size_t KEY_BYTES = (size_t)TILE * sizeof(KeyT);
     static constexpr size_t VAL_BYTES = HAS_VAL ? (size_t)TILE * sizeof(u32) : 0;
     static constexpr size_t WHIST_BYTES = (size_t)WARPS * SAB_RADIX_BINS * sizeof(u32);
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * sizeof(u32);
+    static constexpr size_t MATCH_BYTES = SAB_MATCH_SMEM ? WHIST_BYTES : 0;
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + MATCH_BYTES + SAB_RADIX_BINS * sizeof(u32);
 };
 
 // Digit extractors.  The padding key of a partial tile (all ones) must map to the last bin in use.
@@ -184,7 +193,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
     if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    for (int i = tid; i < WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
+    for (int i = tid; i < (SAB_MATCH_SMEM ? 2 : 1) * WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
     const u64 tile_base = (u64)tile * TILE;
@@ -220,12 +229,23 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
 
     // ---- rank inside the warp (stable in (k, lane) order)
     u32* wh = s_whist + w * SAB_RADIX_BINS;
+    u32* mm = s_whist + (WARPS + w) * SAB_RADIX_BINS;  // mask table of this warp (SAB_MATCH_SMEM only)
+    (void)mm;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 d = dop(keys[k]);
+#if SAB_MATCH_SMEM
+        atomicOr(&mm[d], 1u << lane);
+        __syncwarp();
+        const u32 peers = mm[d];
+        __syncwarp();
+        if ((peers & lanemask_lt()) == 0) mm[d] = 0;  // the leader resets the slot for the next item
+        __syncwarp();
+#else
         const u32 peers = (SAB_HW_MATCH_EVERY > 0 && (k % (SAB_HW_MATCH_EVERY > 0 ? SAB_HW_MATCH_EVERY : 1)) == 0)
                               ? __match_any_sync(SAB_FULL, d)
                               : match_digit(d);
+#endif
         const u32 leader = (u32)(__ffs((int)peers) - 1);
         // The leader's shared-memory atomic returns the running count of this digit in the warp.
         // Atomics of one warp on one address retire in program order, so item k+1 sees item k's
@@ -271,17 +291,25 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     if (tid < SAB_RADIX_BINS) {
         u64 excl = 0;
         if (tile > 0) {
+            // Walk the predecessors SAB_LB_DEPTH at a time: the status loads of one batch are independent,
+            // so a long chain of PARTIAL tiles costs one L2 round trip per batch instead of one per tile.
             i64 t = (i64)tile - 1;
-            while (true) {
-                const u64 v = ld_relaxed_u64(lookback + (u64)t * SAB_RADIX_BINS + tid);
-                const u64 f = v & SAB_LB_FLAG_MASK;
-                if ((v >> SAB_LB_EPOCH_SHIFT) != (u64)epoch || f == 0) {
-                    SAB_SPIN_PAUSE();
-                    continue;
+            bool done = false;
+            while (!done) {
+                u64 v[SAB_LB_DEPTH];
+#pragma unroll
+                for (int j = 0; j < SAB_LB_DEPTH; ++j)
+                    v[j] = (t - j >= 0) ? ld_relaxed_u64(lookback + (u64)(t - j) * SAB_RADIX_BINS + tid) : 0ull;
+#pragma unroll
+                for (int j = 0; j < SAB_LB_DEPTH; ++j) {
+                    if (done) break;
+                    const u64 f = v[j] & SAB_LB_FLAG_MASK;
+                    if ((v[j] >> SAB_LB_EPOCH_SHIFT) != (u64)epoch || f == 0) break;  // not published yet: reload from here
+                    excl += v[j] & SAB_LB_VALUE_MASK;
+                    --t;
+                    if (f == SAB_LB_FLAG_INCLUSIVE) done = true;
                 }
-                excl += v & SAB_LB_VALUE_MASK;
-                if (f == SAB_LB_FLAG_INCLUSIVE) break;
-                --t;
+                if (!done) SAB_SPIN_PAUSE();
             }
             st_relaxed_u64(lb, etag | SAB_LB_FLAG_INCLUSIVE | (excl + (u64)my_count));
         }

@@ -58,6 +58,8 @@ def _bind(L):
         "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
         "sab200_dist_begin": [i32],
         "sab200_dist_end": [i32],
+        "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, vp, vp, i32],
+        "sab200_dist_scatter_p2p": [vp, vp, u64, u32, i32, vp, i32],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -127,6 +129,30 @@ class _Ctx:
         return out
 
 
+_PEER_CACHE = {}
+
+
+def _peer_ranks(cx, B):
+    """The rank[] block of every GPU (B + 1 u32 each), mapped into this process through torch's
+    symmetric memory: returns (local block tensor, uint64 array of the P peer addresses).
+    Cached per (device, P, B): the rendezvous is a collective and not cheap."""
+    key = (str(cx.device), cx.P, B, id(cx.group))
+    if key not in _PEER_CACHE:
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(B + 1, dtype=torch.int32, device=cx.device)
+        hdl = symm.rendezvous(t, cx.group if cx.group is not None else dist.group.WORLD)
+        ptrs = np.array([int(p) for p in hdl.buffer_ptrs], dtype=np.uint64)
+        _PEER_CACHE[key] = (t, ptrs, hdl)
+    t, ptrs, _ = _PEER_CACHE[key]
+    return t, ptrs
+
+
+def _barrier(cx):
+    dist.barrier(group=cx.group)
+    cx.sync()
+    cx.collectives += 1
+
+
 def _to_owner(cx, keys, vals, count, add, B):
     """Stable partition of (keys, vals) by the owner of position keys+add; returns the partitioned
     buffers and the per-destination counts (records whose key is 0xFFFFFFFF are dropped)."""
@@ -147,8 +173,13 @@ def _send_ranks(cx, idx, ranks, count, B, lo, rank_local):
     cx.call("sab200_dist_scatter", _p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev)
 
 
-def dist_saca(shard, n, device, group=None, stats=None):
+def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     """Builds the suffix array of a text of n bytes spread over the ranks of `group`.
+
+    exchange: how rank[] crosses GPUs in the doubling rounds.  "p2p" = the gather / update kernels load
+    and store the owners' blocks directly over NVLink (symmetric memory; no collective in the data path
+    of a round); "nccl" = partition by owner + all_to_all (also the gloo path of the CPU tests);
+    "auto" = p2p on CUDA devices when symmetric memory can be set up, else nccl.
 
     shard: uint8 numpy array or tensor with this rank's text positions [lo, hi) followed by up to HALO
     bytes of the next shard (text[lo : min(n, hi + HALO)], see shard_bounds).
@@ -163,6 +194,19 @@ def dist_saca(shard, n, device, group=None, stats=None):
         raise ValueError("text longer than MAX_LENGTH")
     B, lo, hi = shard_bounds(n, rank, P)
     count = hi - lo
+    use_p2p = False
+    if exchange in ("auto", "p2p") and cx.device.type == "cuda" and n > 0:
+        try:
+            rank_local, peer_ptrs = _peer_ranks(cx, B)
+            use_p2p = True
+        except Exception as e:  # noqa: BLE001 -- any failure to map peers falls back to the collective path
+            if exchange == "p2p":
+                raise
+            use_p2p = False
+    flags = torch.tensor([1 if use_p2p else 0], dtype=torch.int64, device=cx.device)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN, group=cx.group)
+    use_p2p = bool(int(flags.item()))
+    peer_arg = peer_ptrs.ctypes.data_as(C.c_void_p) if use_p2p else None
     cx.call("sab200_dist_begin", cx.dev)
     cx.mark("start")
     d_text = torch.as_tensor(shard, dtype=torch.uint8).to(cx.device)
@@ -235,8 +279,13 @@ def dist_saca(shard, n, device, group=None, stats=None):
     m = m.value
     cx.mark("init_ranks")
     # 5. every rank travels to the owner of its text position
-    rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n (rank 0) if owned
-    _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
+    if use_p2p:
+        rank_local.zero_()  # slot of position n (the empty suffix) must read 0
+        _barrier(cx)        # nobody stores into a block that is still being cleared
+        cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, B, P, peer_arg, cx.dev)
+    else:
+        rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n if owned
+        _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
     del ks, vs, k0, k1, v0, v1, rank_seq
     cx.mark("ranks_to_owners")
     # 6. doubling rounds
@@ -255,15 +304,20 @@ def dist_saca(shard, n, device, group=None, stats=None):
         rounds += 1
         if h > n or rounds > 64:
             raise RuntimeError("prefix doubling did not converge")
-        # requests i+h to the owners, answers back in the same order
-        ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, B)
-        recv = cx.exchange_counts(send)
-        q = cx.all_to_all(ipart, send, recv)
-        ans = cx.empty(q.numel(), torch.int32)
-        cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev)
-        r2 = cx.all_to_all(ans, recv, send)
         key64 = cx.empty(m, torch.int64)
-        cx.call("sab200_dist_make_keys", _p(rpart), _p(r2), m, _p(key64), cx.dev)
+        if use_p2p:
+            # the all_reduce above ordered every rank's previous stores before these loads
+            cx.call("sab200_dist_gather_p2p", _p(cur_r1), _p(cur_idx), m, h, B, P, peer_arg, _p(key64), cx.dev)
+            ipart = cur_idx
+        else:
+            # requests i+h to the owners, answers back in the same order
+            ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, B)
+            recv = cx.exchange_counts(send)
+            q = cx.all_to_all(ipart, send, recv)
+            ans = cx.empty(q.numel(), torch.int32)
+            cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev)
+            r2 = cx.all_to_all(ans, recv, send)
+            cx.call("sab200_dist_make_keys", _p(rpart), _p(r2), m, _p(key64), cx.dev)
         key_tmp = cx.empty(m, torch.int64)
         idx_tmp = cx.empty(m, torch.int32)
         which = cx.call("sab200_dist_sort_pairs", _p(key64), _p(key_tmp), _p(ipart), _p(idx_tmp), m, 32 + rank_bits, cx.dev)
@@ -274,8 +328,12 @@ def dist_saca(shard, n, device, group=None, stats=None):
         upd_r = cx.empty(m, torch.int32)
         kept = C.c_uint64()
         cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
-                                      C.byref(kept), cx.dev)
-        _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
+                C.byref(kept), cx.dev)
+        if use_p2p:
+            _barrier(cx)  # every rank has finished loading ranks of this round
+            cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, B, P, peer_arg, cx.dev)
+        else:
+            _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
@@ -284,6 +342,7 @@ def dist_saca(shard, n, device, group=None, stats=None):
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
+                      "exchange": "p2p" if use_p2p else "collective",
                       "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()},
                       "wall_ms": round((time.perf_counter() - t_enter) * 1e3, 2)})
     return sa_local, sa_off

@@ -45,12 +45,13 @@ def main():
         B, lo, hi = sdist.shard_bounds(n, rank, world)
         shard = t[lo:min(n, hi + sdist.HALO)]
         st = {}
-        sa_local, sa_off = sdist.dist_saca(shard, n, device, stats=st)
+        sa_local, sa_off = sdist.dist_saca(shard, n, device, stats=st, exchange=os.environ.get("SAB_DIST_EXCHANGE", "auto"))
         full = sdist.gather_sa(sa_local, n)
         if rank == 0:
             exp = oracle.saca(t)
             good = bool(np.array_equal(full, exp))
-            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d" % (n, world, st["rounds"], good, st["all_to_all_bytes"]), flush=True)
+            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d exchange=%s" % (n, world, st["rounds"], good, st["all_to_all_bytes"],
+                                                                                st["exchange"]), flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.broadcast(flag, 0)
