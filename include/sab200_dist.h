@@ -89,6 +89,16 @@ int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint
 int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
                                 const uint64_t* peer_rank_ptrs, int32_t device);
 
+/* Key exchange fused into the partition kernel.  count_keys: counts (host, P x u64) per destination.
+ * partition_keys_p2p: the partition pass stores destination d's records straight into GPU d's receive
+ * buffers (peer_key_ptrs[d] / peer_idx_ptrs[d], mapped device addresses) from record offsets[d] on --
+ * no staging copy, no all_to_all; the caller barriers before the buffers are read. */
+int32_t sab200_dist_count_keys(const uint64_t* d_keys, uint64_t count, const uint64_t* splitters, int32_t nsplit,
+                               uint64_t* counts, int32_t device);
+int32_t sab200_dist_partition_keys_p2p(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count,
+                                       const uint64_t* splitters, int32_t nsplit, const uint64_t* offsets,
+                                       const uint64_t* peer_key_ptrs, const uint64_t* peer_idx_ptrs, int32_t device);
+
 /* Bracket one construction on this rank: begin() clears the counters of sab200_get_stats() (and arms
  * per-launch event timing when sab200_set_profiling(1)); end() publishes them. */
 int32_t sab200_dist_begin(int32_t device);

@@ -364,3 +364,53 @@ extern "C" int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t
     SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SAB_OK;
 }
+
+// ------------------------------------------------------------------ key exchange fused into the partition
+// counts only (host, P x u64): how many of the keys go to each destination
+extern "C" int32_t sab200_dist_count_keys(const uint64_t* d_keys, uint64_t count, const uint64_t* splitters, int32_t nsplit,
+                                          uint64_t* counts, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (nsplit < 0 || nsplit > SAB_MAX_RANKS - 1 || !counts) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SplitterDigit dop;
+    dop.np = nsplit;
+    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) dop.s[i] = i < nsplit ? splitters[i] : ~0ull;
+    SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, d_keys, count, dop, nsplit + 1, counts)));
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
+// The partition pass writes destination d's records straight into GPU d's receive buffers
+// (peer_key_ptrs[d], peer_idx_ptrs[d]: device addresses mapped into this process) starting at record
+// offsets[d] (= records the lower ranks send to d): partition and all-to-all in one kernel, the
+// transfer overlapping the ranking tile by tile.  The caller barriers before reading the buffers.
+extern "C" int32_t sab200_dist_partition_keys_p2p(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count,
+                                                  const uint64_t* splitters, int32_t nsplit, const uint64_t* offsets,
+                                                  const uint64_t* peer_key_ptrs, const uint64_t* peer_idx_ptrs,
+                                                  int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (nsplit < 0 || nsplit > SAB_MAX_RANKS - 1 || !offsets || !peer_key_ptrs || !peer_idx_ptrs) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (count == 0) return SAB_OK;
+    SplitterDigit dop;
+    dop.np = nsplit;
+    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) dop.s[i] = i < nsplit ? splitters[i] : ~0ull;
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    u64* h = (u64*)(c->h_small + 1024);
+    for (int i = 0; i < 256; ++i) h[i] = 0;
+    for (int d = 0; d <= nsplit; ++d) {
+        po.k[d] = peer_key_ptrs[d];
+        po.v[d] = peer_idx_ptrs[d];
+        h[d] = offsets[d];
+    }
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->d_gbase, h, 256 * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    constexpr int TILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
+    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
+    SAB_TRY((sab_launch_pass_op<u64, false, SplitterDigit, true>(c, d_keys, (u64*)nullptr, d_idx, (u32*)nullptr, count, dop,
+                                                                  c->d_gbase, &po)));
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}

@@ -119,7 +119,7 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
 #define SAB_MATCH_SMEM 0
 #endif
 #ifndef SAB_LB_DEPTH
-#define SAB_LB_DEPTH 8
+#define SAB_LB_DEPTH 4
 #endif
 __device__ __forceinline__ u32 match_digit(u32 d) {
 #if SAB_MATCH_HW
@@ -174,12 +174,20 @@ struct OwnerDigit {  // owner rank of text position key + add under a block dist
     }
 };
 
+// PEER passes (multi-GPU key exchange fused into the partition): bin d is written to the receive
+// buffers of GPU d -- device addresses mapped into this process (symmetric memory), stores travel
+// over NVLink -- at record offset gbase[d] inside them.
+struct PeerOut {
+    u64 k[SAB_MAX_RANKS];  // key buffer of every destination
+    u64 v[SAB_MAX_RANKS];  // payload buffer of every destination
+};
+
 // vals_in may be null when IOTA_VAL (payload = position of the record in the input).
-template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, int THREADS, int ITEMS>
+template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, bool PEER, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, SAB_ONESWEEP_MIN_BLOCKS)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
                 u32* __restrict__ vals_out, u64 n, DigitOp dop, const u64* __restrict__ gbase,
-                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch) {
+                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch, PeerOut po) {
     typedef OnesweepCfg<KeyT, HAS_VAL, IOTA_VAL, THREADS, ITEMS> Cfg;
     static_assert(THREADS >= SAB_RADIX_BINS && THREADS % 32 == 0, "one look-back lane per bin");
     constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE, WTILE = 32 * ITEMS;
@@ -190,8 +198,14 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     u32* s_whist = s_goff + SAB_RADIX_BINS;                                  // [WARPS][256]
     SAB_SHARED_VAR(u32, s_tile);
     SAB_SHARED_ARRAY(u32, s_wsum, 8);
+    SAB_SHARED_ARRAY(u64, s_pk, SAB_MAX_RANKS);
+    SAB_SHARED_ARRAY(u64, s_pv, SAB_MAX_RANKS);
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    if (PEER && tid < SAB_MAX_RANKS) {
+        s_pk[tid] = po.k[tid];
+        s_pv[tid] = po.v[tid];
+    }
     if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
     for (int i = tid; i < (SAB_MATCH_SMEM ? 2 : 1) * WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
     __syncthreads();
@@ -334,9 +348,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         for (int k = 0; k < ITEMS; ++k) {
             const u32 p = tid + k * THREADS;
             const KeyT key = s_keys[p];
-            const u32 dst = s_goff[dop(key)] + p;
-            keys_out[dst] = key;
-            if (HAS_VAL) vals_out[dst] = s_vals[p];
+            const u32 d = dop(key);
+            const u32 dst = s_goff[d] + p;
+            if (PEER) {
+                ((KeyT*)(uintptr_t)s_pk[d & (SAB_MAX_RANKS - 1)])[dst] = key;
+                if (HAS_VAL) ((u32*)(uintptr_t)s_pv[d & (SAB_MAX_RANKS - 1)])[dst] = s_vals[p];
+            } else {
+                keys_out[dst] = key;
+                if (HAS_VAL) vals_out[dst] = s_vals[p];
+            }
         }
     } else {
 #pragma unroll
@@ -344,9 +364,15 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             const u32 p = tid + k * THREADS;
             if (p < valid) {
                 const KeyT key = s_keys[p];
-                const u32 dst = s_goff[dop(key)] + p;
-                keys_out[dst] = key;
-                if (HAS_VAL) vals_out[dst] = s_vals[p];
+                const u32 d = dop(key);
+                const u32 dst = s_goff[d] + p;
+                if (PEER) {
+                    ((KeyT*)(uintptr_t)s_pk[d & (SAB_MAX_RANKS - 1)])[dst] = key;
+                    if (HAS_VAL) ((u32*)(uintptr_t)s_pv[d & (SAB_MAX_RANKS - 1)])[dst] = s_vals[p];
+                } else {
+                    keys_out[dst] = key;
+                    if (HAS_VAL) vals_out[dst] = s_vals[p];
+                }
             }
         }
     }

@@ -28,9 +28,9 @@ struct PassShape<u32> {
     static constexpr int THREADS = SAB_PASS_THREADS, ITEMS = SAB_PASS_ITEMS;
 };
 
-template <typename KeyT, bool IOTA, typename DigitOp>
+template <typename KeyT, bool IOTA, typename DigitOp, bool PEER = false>
 static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, DigitOp dop,
-                              const u64* gbase) {
+                              const u64* gbase, const PeerOut* peer = nullptr) {
     constexpr int THREADS = PassShape<KeyT>::THREADS, ITEMS = PassShape<KeyT>::ITEMS;
     typedef OnesweepCfg<KeyT, true, IOTA, THREADS, ITEMS> Cfg;
     const u64 tiles = div_up64(n, (u64)Cfg::TILE);
@@ -39,13 +39,16 @@ static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const 
         c->lb_epoch = 0;
     }
     const u32 epoch = ++c->lb_epoch;
-    auto kern = onesweep_kernel<KeyT, DigitOp, true, IOTA, THREADS, ITEMS>;
+    auto kern = onesweep_kernel<KeyT, DigitOp, true, IOTA, PEER, THREADS, ITEMS>;
+    PeerOut po;
+    memset(&po, 0, sizeof(po));
+    if (PEER && peer) po = *peer;
 #ifndef SAB_EMU
     SAB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));  // per device
 #endif
     sab_prof_begin(c, 0);
     SAB_LAUNCH(kern, (unsigned)tiles, THREADS, Cfg::SMEM, c->stream, kin, kout, vin, vout, n, dop, gbase,
-               c->d_lookback, c->d_ticket, c->ticket_host, epoch);
+               c->d_lookback, c->d_ticket, c->ticket_host, epoch, po);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     c->ticket_host += (u32)tiles;

@@ -59,6 +59,8 @@ def _bind(L):
         "sab200_dist_begin": [i32],
         "sab200_dist_end": [i32],
         "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, vp, vp, i32],
+        "sab200_dist_count_keys": [vp, u64, vp, i32, vp, i32],
+        "sab200_dist_partition_keys_p2p": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
         "sab200_dist_scatter_p2p": [vp, vp, u64, u32, i32, vp, i32],
     }
     for name, args in sig.items():
@@ -130,6 +132,22 @@ class _Ctx:
 
 
 _PEER_CACHE = {}
+
+
+def _peer_recv(cx, cap):
+    """Symmetric receive buffers of the fused key exchange: `cap` (key u64, index u32) records per GPU.
+    Returns (keys tensor, idx tensor, peer key addresses, peer idx addresses)."""
+    key = ("recv", str(cx.device), cx.P, cap, id(cx.group))
+    if key not in _PEER_CACHE:
+        import torch.distributed._symmetric_memory as symm
+        grp = cx.group if cx.group is not None else dist.group.WORLD
+        tk = symm.empty(cap, dtype=torch.int64, device=cx.device)
+        hk = symm.rendezvous(tk, grp)
+        ti = symm.empty(cap, dtype=torch.int32, device=cx.device)
+        hi = symm.rendezvous(ti, grp)
+        _PEER_CACHE[key] = (tk, ti, np.array([int(p) for p in hk.buffer_ptrs], dtype=np.uint64),
+                            np.array([int(p) for p in hi.buffer_ptrs], dtype=np.uint64), hk, hi)
+    return _PEER_CACHE[key][:4]
 
 
 def _peer_ranks(cx, B):
@@ -245,17 +263,43 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         splitters[i] = pool[min(pool.size - 1, (i + 1) * pool.size // P)] if pool.size else 0
     cx.mark("pack+splitters")
     # 3. partition by destination, exchange
-    kp = cx.empty(count, torch.int64)
-    ip = cx.empty(count, torch.int32)
-    cnt = np.zeros(P, dtype=np.uint64)
-    cx.call("sab200_dist_partition_keys", _p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
-                                          cnt.ctypes.data_as(C.c_void_p), cx.dev)
-    cx.mark("partition_keys")
-    send = [int(x) for x in cnt]
-    recv = cx.exchange_counts(send)
-    k0 = cx.all_to_all(kp, send, recv)
-    v0 = cx.all_to_all(ip, send, recv)
-    del keys, idx, kp, ip
+    k0 = v0 = None
+    if use_p2p:
+        # fused: the partition kernel stores each record straight into its destination GPU
+        cnt = np.zeros(P, dtype=np.uint64)
+        cx.call("sab200_dist_count_keys", _p(keys), count, splitters.ctypes.data_as(C.c_void_p), P - 1,
+                cnt.ctypes.data_as(C.c_void_p), cx.dev)
+        mine = torch.tensor([int(x) for x in cnt], dtype=torch.int64, device=cx.device)
+        allc = [torch.empty_like(mine) for _ in range(P)]
+        dist.all_gather(allc, mine, group=cx.group)
+        cx.collectives += 1
+        mat = np.stack([a.cpu().numpy() for a in allc])          # mat[src][dst]
+        recv_tot = mat.sum(axis=0)
+        cap = int(1.25 * B) + 4096
+        if int(recv_tot.max()) <= cap:
+            rk, ri, pk, pi = _peer_recv(cx, cap)
+            offs = np.ascontiguousarray(mat[:rank].sum(axis=0) if rank else np.zeros(P, dtype=np.int64)).astype(np.uint64)
+            _barrier(cx)  # every rank is done with the previous contents of its receive buffers
+            cx.mark("partition_keys")
+            cx.call("sab200_dist_partition_keys_p2p", _p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1,
+                    offs.ctypes.data_as(C.c_void_p), pk.ctypes.data_as(C.c_void_p), pi.ctypes.data_as(C.c_void_p), cx.dev)
+            _barrier(cx)  # all peers have finished storing into this rank's buffers
+            Rn = int(recv_tot[rank])
+            k0, v0 = rk[:Rn], ri[:Rn]
+            cx.a2a_bytes += count * 12
+    if k0 is None:
+        kp = cx.empty(count, torch.int64)
+        ip = cx.empty(count, torch.int32)
+        cnt = np.zeros(P, dtype=np.uint64)
+        cx.call("sab200_dist_partition_keys", _p(keys), _p(idx), count, splitters.ctypes.data_as(C.c_void_p), P - 1, _p(kp), _p(ip),
+                cnt.ctypes.data_as(C.c_void_p), cx.dev)
+        cx.mark("partition_keys")
+        send = [int(x) for x in cnt]
+        recv = cx.exchange_counts(send)
+        k0 = cx.all_to_all(kp, send, recv)
+        v0 = cx.all_to_all(ip, send, recv)
+        del kp, ip
+    del keys, idx
     R = k0.numel()
     cx.mark("exchange_keys")
     # 4. local sort: this rank's slice of the suffix array
