@@ -48,6 +48,15 @@ def make_text(workload, n, seed_shift=0):
     return fn(n, seed)
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -261,7 +270,10 @@ def main():
                        "rounds": stats["rounds"], "radix_passes": stats["passes"], "active": stats["active"],
                        "sigma": stats["sigma"], "symbols_per_key": stats["symbols_per_key"]},
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel<u64,u32> (LSD radix pass)", "achieved": round(achieved, 1),
-                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": (measured_traffic() or {}).get("traffic") if args.workload == "c2" and not args.n_mib else None,
+                         "traffic_note": "DRAM read+write bytes of one full-size pass (m = 2^30 records, algorithmic "
+                                         "25.77e9 B) from the committed ncu capture, profiles/r01_traffic.json",
                          "peak_source": peak_src, "bytes_per_record": 24, "launches": int(pass_launches),
                          "avg_launch_ms": round(pass_ms / max(1, pass_launches), 4),
                          "share_of_step": round(pass_ms / args.steps / dev_ms, 3)},

@@ -103,6 +103,17 @@ def test_queries_vs_oracle(gpu_lib, oracle):
     pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
 
 
+def test_queries_sharded_over_replicas(gpu_lib, oracle):
+    # the index is replicated, the patterns are sharded over the GPUs, no collective
+    ngpus = min(4, gpu_lib.sab200_device_count())
+    if ngpus < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rng = np.random.default_rng(7)
+    s = gen.dna_like(1 << 20)
+    pats = pc.random_patterns(rng, s, 5001, max_len=64)
+    pc.check_queries(oracle, s, pats, ngpus=ngpus)
+
+
 def test_baseline_shapes_16mib_bit_exact(gpu_lib, oracle):
     # the named shapes at a size the oracle finishes in seconds: bit-exact
     n = 16 << 20
