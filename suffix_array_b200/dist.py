@@ -27,6 +27,10 @@ import torch.distributed as dist
 from . import _lib
 
 HALO = 64
+# Above this many records per rank an exchange goes through partition + all_to_all (bulk NVLink
+# transfers, local random access); below it the kernels load / store the owners' blocks directly
+# (no collective, but 4-byte remote accesses).  Measured cross-over on 8 B200: a few 10^7 records.
+P2P_MAX_RECORDS = int(__import__("os").environ.get("SAB_P2P_MAX_RECORDS", 16 << 20))
 
 
 def shard_bounds(n, rank, world):
@@ -326,7 +330,10 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     if use_p2p:
         rank_local.zero_()  # slot of position n (the empty suffix) must read 0
         _barrier(cx)        # nobody stores into a block that is still being cleared
-        cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, B, P, peer_arg, cx.dev)
+        if B <= P2P_MAX_RECORDS:
+            cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, B, P, peer_arg, cx.dev)
+        else:
+            _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
     else:
         rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n if owned
         _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
@@ -349,7 +356,8 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         if h > n or rounds > 64:
             raise RuntimeError("prefix doubling did not converge")
         key64 = cx.empty(m, torch.int64)
-        if use_p2p:
+        p2p_round = use_p2p and tot <= P2P_MAX_RECORDS * P  # same decision on every rank
+        if p2p_round:
             # the all_reduce above ordered every rank's previous stores before these loads
             cx.call("sab200_dist_gather_p2p", _p(cur_r1), _p(cur_idx), m, h, B, P, peer_arg, _p(key64), cx.dev)
             ipart = cur_idx
@@ -373,7 +381,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         kept = C.c_uint64()
         cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
                 C.byref(kept), cx.dev)
-        if use_p2p:
+        if p2p_round:
             _barrier(cx)  # every rank has finished loading ranks of this round
             cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, B, P, peer_arg, cx.dev)
         else:
