@@ -143,6 +143,8 @@ def _peer_recv(cx, cap):
     Returns (keys tensor, idx tensor, peer key addresses, peer idx addresses)."""
     key = ("recv", str(cx.device), cx.P, cap, id(cx.group))
     if key not in _PEER_CACHE:
+        for old in [k_ for k_ in _PEER_CACHE if k_[0] == "recv"]:  # one live set of receive buffers
+            del _PEER_CACHE[old]
         import torch.distributed._symmetric_memory as symm
         grp = cx.group if cx.group is not None else dist.group.WORLD
         tk = symm.empty(cap, dtype=torch.int64, device=cx.device)
@@ -158,8 +160,10 @@ def _peer_ranks(cx, B):
     """The rank[] block of every GPU (B + 1 u32 each), mapped into this process through torch's
     symmetric memory: returns (local block tensor, uint64 array of the P peer addresses).
     Cached per (device, P, B): the rendezvous is a collective and not cheap."""
-    key = (str(cx.device), cx.P, B, id(cx.group))
+    key = ("rank", str(cx.device), cx.P, B, id(cx.group))
     if key not in _PEER_CACHE:
+        for old in [k_ for k_ in _PEER_CACHE if k_[0] == "rank"]:
+            del _PEER_CACHE[old]
         import torch.distributed._symmetric_memory as symm
         t = symm.empty(B + 1, dtype=torch.int32, device=cx.device)
         hdl = symm.rendezvous(t, cx.group if cx.group is not None else dist.group.WORLD)
@@ -280,7 +284,10 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         mat = np.stack([a.cpu().numpy() for a in allc])          # mat[src][dst]
         recv_tot = mat.sum(axis=0)
         cap = int(1.25 * B) + 4096
-        if int(recv_tot.max()) <= cap:
+        # the symmetric receive buffers stay allocated between calls: only use them when they are a small
+        # part of the device memory (3.9 GiB on 2 GPUs needs every byte for the rounds)
+        roomy = cap * 12 <= 0.12 * torch.cuda.get_device_properties(cx.device).total_memory
+        if roomy and int(recv_tot.max()) <= cap:
             rk, ri, pk, pi = _peer_recv(cx, cap)
             offs = np.ascontiguousarray(mat[:rank].sum(axis=0) if rank else np.zeros(P, dtype=np.int64)).astype(np.uint64)
             _barrier(cx)  # every rank is done with the previous contents of its receive buffers
