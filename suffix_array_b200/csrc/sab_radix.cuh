@@ -191,11 +191,13 @@ struct TextKeySrc {
 #define SAB_HTEXT_THREADS 512
 #define SAB_HTEXT_ITEMS 8
 #define SAB_HTEXT_TILE (SAB_HTEXT_THREADS * SAB_HTEXT_ITEMS)
+#define SAB_HTEXT_CPAD(o) ((o) + (((o) >> 3) << 1))
 
 __global__ void __launch_bounds__(SAB_HTEXT_THREADS)
 radix_hist_text_kernel(TextKeySrc ts, u64 count, int begin_bit, int npass, u64* __restrict__ ghist) {
     SAB_SHARED_ARRAY(u32, s_hist, SAB_MAX_PASSES * SAB_RADIX_BINS);
-    SAB_SHARED_ARRAY(u16, s_code, SAB_HTEXT_TILE + 64);
+    // codes padded by one word per 8 elements: thread t starts at word 5t, conflict-free
+    SAB_SHARED_ARRAY(u16, s_code, SAB_HTEXT_CPAD(SAB_HTEXT_TILE + 64) + 8);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
     for (int i = threadIdx.x; i < SAB_MAX_PASSES * SAB_RADIX_BINS; i += SAB_HTEXT_THREADS) s_hist[i] = 0;
     if (threadIdx.x < 256) s_lut[threadIdx.x] = ts.lut[threadIdx.x];
@@ -205,19 +207,19 @@ radix_hist_text_kernel(TextKeySrc ts, u64 count, int begin_bit, int npass, u64* 
         const u64 base = t * SAB_HTEXT_TILE;
         for (int o = threadIdx.x; o < SAB_HTEXT_TILE + 64; o += SAB_HTEXT_THREADS) {
             const u64 i = base + o;
-            s_code[o] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
+            s_code[SAB_HTEXT_CPAD(o)] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
         }
         __syncthreads();
         const int o0 = threadIdx.x * SAB_HTEXT_ITEMS;
         u64 key = 0;
-        for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[o0 + q];
+        for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_HTEXT_CPAD(o0 + q)];
 #pragma unroll
         for (int j = 0; j < SAB_HTEXT_ITEMS; ++j) {
             if (base + o0 + j < count) {
                 for (int p = 0; p < npass; ++p)
                     atomicAdd(&s_hist[p * SAB_RADIX_BINS + ((u32)(key >> (begin_bit + p * SAB_RADIX_BITS)) & 0xffu)], 1u);
             }
-            key = (key - (u64)s_code[o0 + j] * ts.top) * ts.radix + (u64)s_code[o0 + j + ts.k];
+            key = (key - (u64)s_code[SAB_HTEXT_CPAD(o0 + j)] * ts.top) * ts.radix + (u64)s_code[SAB_HTEXT_CPAD(o0 + j + ts.k)];
         }
         __syncthreads();
     }
@@ -254,7 +256,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     SAB_SHARED_ARRAY(u64, s_pk, SAB_MAX_RANKS);
     SAB_SHARED_ARRAY(u64, s_pv, SAB_MAX_RANKS);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
-    static_assert(!TEXT || (sizeof(KeyT) == 8 && IOTA_VAL && (size_t)(THREADS * ITEMS + 64) * 2 <= Cfg::KEY_BYTES),
+    static_assert(!TEXT || (sizeof(KeyT) == 8 && IOTA_VAL && (size_t)(THREADS * ITEMS + 64) * 2 * (ITEMS + 2) / ITEMS + 64 <= Cfg::KEY_BYTES),
                   "TEXT passes build u64 keys with iota payload; the codes are staged in the key area");
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
@@ -282,20 +284,21 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     if (TEXT) {
         // keys from the text: lane l of warp w owns ITEMS consecutive positions
         u16* s_code = (u16*)smem;
+#define SAB_TCPAD(o) ((o) + (((o) / ITEMS) << 1))  // one pad word per lane chunk: lane l starts at word l*(ITEMS/2+1)
         for (int o = tid; o < TILE + 64; o += THREADS) {
             const u64 i = tile_base + o;
-            s_code[o] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
+            s_code[SAB_TCPAD(o)] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
         }
         __syncthreads();
         if (full) {
             const u32 o0 = w * WTILE + lane * ITEMS;
             u64 key = 0;
-            for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[o0 + q];
+            for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_TCPAD(o0 + q)];
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 keys[k] = (KeyT)key;
                 vals[k] = (u32)(tile_base + o0 + k);
-                key = (key - (u64)s_code[o0 + k] * ts.top) * ts.radix + (u64)s_code[o0 + k + ts.k];
+                key = (key - (u64)s_code[SAB_TCPAD(o0 + k)] * ts.top) * ts.radix + (u64)s_code[SAB_TCPAD(o0 + k + ts.k)];
             }
         } else {
             // last tile: warp-striped like every other pass, so the padding records rank behind all real
@@ -304,7 +307,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             for (int k = 0; k < ITEMS; ++k) {
                 const u32 o = wofs + k * 32;
                 u64 key = 0;
-                for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[o + q];
+                for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_TCPAD(o + q)];
                 keys[k] = o < valid ? (KeyT)key : KeyTraits<KeyT>::max_key();
                 vals[k] = (u32)(tile_base + o);
             }
