@@ -113,6 +113,19 @@ int32_t sab200_search_lcp_batch(sab200_index* ix, const uint8_t* pats, const uin
 int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t np,
                                        uint32_t* d_lo, uint32_t* d_hi);
 
+/* ---- pack serialisation --------------------------------------------------------------------
+ * Replaces PackedSuffixArray::from_sa + dump_bytes and load_bytes + into_sa (src/packed_sa.rs:17-88,
+ * 99-124; behind SuffixArray::dump* / load*, src/sa.rs:256-361, feature "pack"): bincode little-endian
+ * header (magic "SA4x", length, data length) + BitPacker4x blocks of 128 values at
+ * bits = 32 - clz(length - 1), trailing zero bytes of the last block dropped.  Host buffers.
+ * sab200_pack_bound(len) bytes always suffice for sab200_pack.  The reference's two latent faults on
+ * load (length 1; fully trimmed last block) are guarded, not reproduced.  Byte parity
+ * with the bitpacking/bincode crates is unpinned (they are not in the reference tree; its test only
+ * checks the round trip, src/tests.rs:63-76). */
+uint64_t sab200_pack_bound(uint64_t sa_len);
+int32_t sab200_pack(const uint32_t* sa, uint64_t sa_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
+int32_t sab200_unpack(const uint8_t* bytes, uint64_t nbytes, uint32_t* sa, uint64_t sa_cap, uint64_t* sa_len);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 int32_t sab200_get_stats(sab200_stats* out);
 void sab200_set_profiling(int32_t on); /* per-launch CUDA events for the stats above */

@@ -58,6 +58,12 @@ def lib():
         L.oracle_contains_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_uint64, C.c_void_p]
         L.oracle_contains_batch.restype = None
+        L.oracle_pack_bound.argtypes = [C.c_uint64]
+        L.oracle_pack_bound.restype = C.c_uint64
+        L.oracle_pack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        L.oracle_pack.restype = C.c_uint64
+        L.oracle_unpack.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.oracle_unpack.restype = C.c_uint64
         L.oracle_naive_contains.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         L.oracle_naive_contains.restype = C.c_int
         L.oracle_naive_search_all.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -184,3 +190,26 @@ def naive_search_all(s, pat):
 def naive_search_lcp(s, pat):
     t, p = _bytes(s), _bytes(pat)
     return int(lib().oracle_naive_search_lcp(_p(t), t.size, _p(p), p.size))
+
+
+def pack(sa):
+    """src/packed_sa.rs:17-53,99-106 -> bytes"""
+    sa = np.ascontiguousarray(sa, dtype=np.uint32)
+    out = np.empty(int(lib().oracle_pack_bound(sa.size)), dtype=np.uint8)
+    n = lib().oracle_pack(_p(sa), sa.size, _p(out))
+    if n == 0:
+        raise ValueError("oracle_pack failed")
+    return out[:n].tobytes()
+
+
+def unpack(data):
+    """src/packed_sa.rs:55-88,117-124 -> np.uint32[length]; ValueError on malformed input"""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    if buf.size < 16:
+        raise ValueError("truncated")
+    length = int(np.frombuffer(buf[4:8].tobytes(), dtype="<u4")[0])
+    sa = np.empty(max(length, 1), dtype=np.uint32)
+    n = lib().oracle_unpack(_p(buf), buf.size, _p(sa), sa.size)
+    if n == 2 ** 64 - 1:
+        raise ValueError("malformed packed suffix array")
+    return sa[:n].copy()

@@ -102,6 +102,9 @@ def _bind(L):
         "sab200_contains_batch": ([vp, vp, vp, u64, vp], i32),
         "sab200_search_lcp_batch": ([vp, vp, vp, u64, vp, vp], i32),
         "sab200_search_all_batch_device": ([vp, vp, vp, u64, vp, vp], i32),
+        "sab200_pack_bound": ([u64], u64),
+        "sab200_pack": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
+        "sab200_unpack": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
     }
     for name, (args, res) in _opt.items():
         f = getattr(L, name)

@@ -5,6 +5,7 @@
 #include "sab_context.cuh"
 #include "sab_saca.cuh"
 #include "sab_search.cuh"
+#include "sab_pack.cuh"
 
 #include <chrono>
 #include <cstdlib>
@@ -571,6 +572,88 @@ extern "C" int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_
     SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
     SAB_TRY(launch_search<0>(r, ix->n, d_pats, d_offs, np, d_lo, d_hi));
     SAB_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+    return SAB_OK;
+}
+
+// ---- pack serialisation ---------------------------------------------------------------------
+extern "C" uint64_t sab200_pack_bound(uint64_t sa_len) { return 16 + ((sa_len + 127) / 128) * 512; }
+
+extern "C" int32_t sab200_pack(const uint32_t* sa, uint64_t sa_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+    if (!sa || !out || !out_len || sa_len == 0 || sa_len > 0xffffffffull) {  // src/packed_sa.rs:18
+        sab_set_error("sab200_pack: bad arguments");
+        return SAB_ERR_ARGS;
+    }
+    const unsigned bits = sab_pack_bits(sa_len);
+    const u64 blocks = (sa_len + 127) / 128;
+    const u64 words = blocks * 4ull * bits;
+    if (out_cap < 16 + words * 4) {
+        sab_set_error("sab200_pack: output buffer too small (need %llu bytes)", (unsigned long long)(16 + words * 4));
+        return SAB_ERR_ARGS;
+    }
+    SabContext* c = sab_get_context(0);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t in_bytes = sab_align_up((size_t)sa_len * 4 + 64, 256);
+    SAB_TRY(sab_arena_reserve(c, in_bytes + (size_t)words * 4 + 1024));
+    u32* d_sa = (u32*)c->arena;
+    u32* d_out = (u32*)(c->arena + in_bytes);
+    cudaStream_t st = c->stream;
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_sa, sa, sa_len * 4, cudaMemcpyHostToDevice, st));
+    if (words) {
+        SAB_LAUNCH(pack_blocks_kernel, (unsigned)div_up64(words, 256), 256, 0, st, (const u32*)d_sa, sa_len, bits, words, d_out);
+        SAB_LAUNCH_CHECK();
+        SAB_CUDA_TRY(cudaMemcpyAsync(out + 16, d_out, words * 4, cudaMemcpyDeviceToHost, st));
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    u64 data_len = words * 4;
+    if (sa_len % 128 != 0) {  // src/packed_sa.rs:41-45: trailing zero bytes of the padded last block are dropped
+        const u64 chunk = 16ull * bits, start = data_len - chunk;
+        u64 t = chunk;
+        while (t > 0 && out[16 + start + t - 1] == 0) --t;
+        data_len = start + t;
+    }
+    const u32 magic = SAB_PACK_MAGIC, length = (u32)sa_len;
+    memcpy(out, &magic, 4);
+    memcpy(out + 4, &length, 4);
+    memcpy(out + 8, &data_len, 8);
+    *out_len = 16 + data_len;
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_unpack(const uint8_t* bytes, uint64_t nbytes, uint32_t* sa, uint64_t sa_cap, uint64_t* sa_len) {
+    if (!bytes || !sa || !sa_len || nbytes < 16) {
+        sab_set_error("sab200_unpack: bad arguments");
+        return SAB_ERR_ARGS;
+    }
+    u32 magic, length;
+    u64 dlen;
+    memcpy(&magic, bytes, 4);
+    memcpy(&length, bytes + 4, 4);
+    memcpy(&dlen, bytes + 8, 8);
+    const unsigned bits = sab_pack_bits(length);
+    const u64 blocks = ((u64)length + 127) / 128, words = blocks * 4ull * bits;
+    if (magic != SAB_PACK_MAGIC || dlen != nbytes - 16 || dlen > words * 4 || length == 0 || length > sa_cap) {
+        sab_set_error("sab200_unpack: not a packed suffix array (magic %08x, length %u, %llu data bytes)", magic, length,
+                      (unsigned long long)dlen);
+        return SAB_ERR_ARGS;
+    }
+    SabContext* c = sab_get_context(0);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t in_bytes = sab_align_up((size_t)words * 4 + 64, 256);
+    SAB_TRY(sab_arena_reserve(c, in_bytes + (size_t)length * 4 + 1024));
+    u32* d_in = (u32*)c->arena;
+    u32* d_sa = (u32*)(c->arena + in_bytes);
+    cudaStream_t st = c->stream;
+    SAB_CUDA_TRY(cudaMemsetAsync(d_in, 0, in_bytes, st));  // re-pads the trimmed tail (src/packed_sa.rs:80-85)
+    if (dlen) SAB_CUDA_TRY(cudaMemcpyAsync(d_in, bytes + 16, dlen, cudaMemcpyHostToDevice, st));
+    SAB_LAUNCH(unpack_blocks_kernel, (unsigned)div_up64(length, 256), 256, 0, st, (const u32*)d_in, (u64)length, bits, d_sa);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaMemcpyAsync(sa, d_sa, (size_t)length * 4, cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    *sa_len = length;
     return SAB_OK;
 }
 

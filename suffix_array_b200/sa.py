@@ -191,6 +191,70 @@ class SuffixArray:
         st, en = self.search_lcp_batch([pat])
         return range(int(st[0]), int(en[0]))
 
+    # ---- pack serialisation (feature "pack": src/sa.rs:256-361 over src/packed_sa.rs)
+    def dump_bytes(self):
+        """src/sa.rs:275-278 -> bytes (bincode header + BitPacker4x blocks, packed on the GPU)."""
+        L = _lib.require_gpu()
+        cap = int(L.sab200_pack_bound(self.sa.size))
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_uint64()
+        _lib.check(L.sab200_pack(self.sa.ctypes.data_as(C.c_void_p), self.sa.size, out.ctypes.data_as(C.c_void_p), cap,
+                                 C.byref(n)), "sab200_pack")
+        return out[:n.value].tobytes()
+
+    def dump(self, file):
+        """src/sa.rs:257-260: writes to a binary file object."""
+        file.write(self.dump_bytes())
+
+    def dump_file(self, name):
+        """src/sa.rs:264-271"""
+        with open(name, "wb") as f:
+            self.dump(f)
+
+    @classmethod
+    def unchecked_load_bytes(cls, s, data):
+        """src/sa.rs:338-346: no integrity check.  Malformed input raises ValueError (io::Error in the reference)."""
+        L = _lib.require_gpu()
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        if buf.size < 16:
+            raise ValueError("truncated packed suffix array")
+        length = int(np.frombuffer(buf[4:8].tobytes(), dtype="<u4")[0])
+        sa = np.empty(max(length, 1), dtype=np.uint32)
+        n = C.c_uint64()
+        rc = L.sab200_unpack(buf.ctypes.data_as(C.c_void_p), buf.size, sa.ctypes.data_as(C.c_void_p), sa.size, C.byref(n))
+        if rc == -1:
+            raise ValueError(L.sab200_last_error().decode("utf-8", "replace"))
+        _lib.check(rc, "sab200_unpack")
+        return cls.unchecked_from_parts(s, sa[:n.value])
+
+    @classmethod
+    def load_bytes(cls, s, data):
+        """src/sa.rs:349-361: ValueError("inconsistent suffix array") where the reference returns InvalidData."""
+        obj = cls.unchecked_load_bytes(s, data)
+        if cls.from_parts(obj.s, obj.sa) is None:
+            raise ValueError("inconsistent suffix array")
+        return obj
+
+    @classmethod
+    def unchecked_load(cls, s, file):
+        return cls.unchecked_load_bytes(s, file.read())
+
+    @classmethod
+    def load(cls, s, file):
+        """src/sa.rs:293-305"""
+        return cls.load_bytes(s, file.read())
+
+    @classmethod
+    def unchecked_load_file(cls, s, name):
+        with open(name, "rb") as f:
+            return cls.unchecked_load(s, f)
+
+    @classmethod
+    def load_file(cls, s, name):
+        """src/sa.rs:323-335"""
+        with open(name, "rb") as f:
+            return cls.load(s, f)
+
     # ---- conversions (src/sa.rs:364-374)
     def __array__(self, dtype=None, copy=None):
         return self.sa if dtype is None else self.sa.astype(dtype)

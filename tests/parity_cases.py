@@ -146,3 +146,34 @@ def sampled_order_check(s, sa, samples=200000, seed=0):
         x = (tb[a:a + 4096] if tb is not None else s[a:a + 4096].tobytes())
         y = (tb[b:b + 4096] if tb is not None else s[b:b + 4096].tobytes())
         assert x < y or (x == y and len(x) == 4096), (int(j), a, b)
+
+
+def check_pack(oracle, s):
+    """pack_correctness (src/tests.rs:63-76): load_bytes(dump_bytes()) round-trips, dump == dump_bytes; plus
+    byte equality with the oracle's restatement of the format and loading of the oracle's bytes."""
+    import io
+    s = np.ascontiguousarray(s, dtype=np.uint8)
+    sa1 = SuffixArray(s)
+    b1 = sa1.dump_bytes()
+    f = io.BytesIO()
+    sa1.dump(f)
+    assert f.getvalue() == b1
+    assert b1 == oracle.pack(sa1.sa), "packed bytes differ from the oracle (n=%d)" % s.size
+    sa2 = SuffixArray.load_bytes(s, b1)
+    assert np.array_equal(sa1.sa, sa2.sa)
+    assert np.array_equal(oracle.unpack(b1), sa1.sa)
+    if s.size >= 2:
+        bad = bytearray(b1)
+        bad[0] ^= 0xFF  # magic
+        try:
+            SuffixArray.unchecked_load_bytes(s, bytes(bad))
+            raise AssertionError("corrupt magic accepted")
+        except ValueError:
+            pass
+        other = np.roll(s, 1)
+        if not np.array_equal(other, s):
+            try:
+                SuffixArray.load_bytes(other, b1)
+                raise AssertionError("suffix array of another text accepted")
+            except ValueError:
+                pass

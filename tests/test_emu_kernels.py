@@ -50,3 +50,16 @@ def test_emu_from_parts(emu_backend, oracle):
     rng = np.random.default_rng(3)
     for n in (0, 1, 2, 50, 3000):
         pc.check_from_parts(oracle, rng.integers(0, 4, n, dtype=np.uint8))
+
+
+def test_emu_pack(emu_backend, oracle):
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 5, 126, 127, 128, 129, 255, 256, 1000, 5000):
+        pc.check_pack(oracle, rng.integers(0, 256, n, dtype=np.uint8))
+    pc.check_pack(oracle, np.frombuffer(b"banana", dtype=np.uint8))
+    assert SuffixArrayBanana().hex() == "53413478070000000d0000000000000006000000250000001300000001"
+
+
+def SuffixArrayBanana():
+    from suffix_array_b200 import SuffixArray
+    return SuffixArray(b"banana").dump_bytes()

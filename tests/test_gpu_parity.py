@@ -114,6 +114,15 @@ def test_queries_sharded_over_replicas(gpu_lib, oracle):
     pc.check_queries(oracle, s, pats, ngpus=ngpus)
 
 
+def test_pack_correctness(gpu_lib, oracle):
+    # src/tests.rs:63-76 (feature "pack") + byte equality with the oracle's restatement of the format
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 127, 128, 129, 4095, 4096, 100000):
+        pc.check_pack(oracle, rng.integers(0, 256, n, dtype=np.uint8))
+    pc.check_pack(oracle, gen.dna_like(3 << 20))
+    assert SuffixArray(b"banana").dump_bytes().hex() == "53413478070000000d0000000000000006000000250000001300000001"
+
+
 def test_baseline_shapes_16mib_bit_exact(gpu_lib, oracle):
     # the named shapes at a size the oracle finishes in seconds: bit-exact
     n = 16 << 20
