@@ -11,6 +11,8 @@
 // methods are the intended fast path.  No method has a CPU fallback.
 #pragma once
 #include <cstdint>
+#include <fstream>
+#include <iterator>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -81,6 +83,62 @@ class SuffixArray {
     static SuffixArray unchecked_from_parts(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t> sa) {
         return SuffixArray(s, n, std::move(sa));
     }
+    // ---- pack serialisation (feature "pack", src/sa.rs:256-361); io errors -> std::runtime_error
+    std::vector<std::uint8_t> dump_bytes() const {  // src/sa.rs:275-278
+        std::vector<std::uint8_t> out(sab200_pack_bound(sa_.size()));
+        std::uint64_t len = 0;
+        check(sab200_pack(sa_.data(), sa_.size(), out.data(), out.size(), &len), "sab200_pack");
+        out.resize(len);
+        return out;
+    }
+    void dump(std::ostream& file) const {  // src/sa.rs:257-260
+        const auto b = dump_bytes();
+        file.write(reinterpret_cast<const char*>(b.data()), (std::streamsize)b.size());
+        if (!file) throw std::runtime_error("dump: write failed");
+    }
+    void dump_file(const std::string& name) const {  // src/sa.rs:264-271
+        std::ofstream f(name, std::ios::binary | std::ios::trunc);
+        if (!f) throw std::runtime_error("dump_file: cannot create " + name);
+        dump(f);
+    }
+    // src/sa.rs:338-346
+    static SuffixArray unchecked_load_bytes(const std::uint8_t* s, std::size_t n, const std::uint8_t* bytes,
+                                            std::size_t nbytes) {
+        if (nbytes < 16) throw std::runtime_error("load: truncated packed suffix array");
+        const std::uint32_t length = (std::uint32_t)bytes[4] | (std::uint32_t)bytes[5] << 8 |
+                                     (std::uint32_t)bytes[6] << 16 | (std::uint32_t)bytes[7] << 24;
+        std::vector<std::uint32_t> sa(length ? length : 1);
+        std::uint64_t len = 0;
+        check(sab200_unpack(bytes, nbytes, sa.data(), sa.size(), &len), "sab200_unpack");
+        sa.resize(len);
+        return SuffixArray(s, n, std::move(sa));
+    }
+    // src/sa.rs:349-361: InvalidData("inconsistent suffix array") -> std::runtime_error
+    static SuffixArray load_bytes(const std::uint8_t* s, std::size_t n, const std::uint8_t* bytes, std::size_t nbytes) {
+        SuffixArray t = unchecked_load_bytes(s, n, bytes, nbytes);
+        auto ok = from_parts(s, n, std::move(t.sa_));
+        if (!ok) throw std::runtime_error("inconsistent suffix array");
+        return std::move(*ok);
+    }
+    static SuffixArray load(const std::uint8_t* s, std::size_t n, std::istream& file) {  // src/sa.rs:293-305
+        const std::vector<std::uint8_t> b((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+        return load_bytes(s, n, b.data(), b.size());
+    }
+    static SuffixArray unchecked_load(const std::uint8_t* s, std::size_t n, std::istream& file) {  // src/sa.rs:281-290
+        const std::vector<std::uint8_t> b((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
+        return unchecked_load_bytes(s, n, b.data(), b.size());
+    }
+    static SuffixArray load_file(const std::uint8_t* s, std::size_t n, const std::string& name) {  // src/sa.rs:323-335
+        std::ifstream f(name, std::ios::binary);
+        if (!f) throw std::runtime_error("load_file: cannot open " + name);
+        return load(s, n, f);
+    }
+    static SuffixArray unchecked_load_file(const std::uint8_t* s, std::size_t n, const std::string& name) {
+        std::ifstream f(name, std::ios::binary);
+        if (!f) throw std::runtime_error("load_file: cannot open " + name);
+        return unchecked_load(s, n, f);
+    }
+
     // src/sa.rs:89-119
     void enable_buckets() {
         if (has_bkt_) return;

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <sstream>
 #include <vector>
 
 #include "sab200_suffix_array.hpp"
@@ -57,6 +58,23 @@ int main() {
             std::vector<std::uint32_t> bad = sa.sa();
             std::swap(bad[1], bad[2]);
             EXPECT(!SuffixArray::from_parts(s.data(), n, bad).has_value());
+        }
+        {  // pack_correctness (src/tests.rs:63-76)
+            const auto bytes = sa.dump_bytes();
+            std::ostringstream os;
+            sa.dump(os);
+            const std::string o = os.str();
+            EXPECT(o.size() == bytes.size() && std::equal(bytes.begin(), bytes.end(), (const std::uint8_t*)o.data()));
+            auto back = SuffixArray::load_bytes(s.data(), n, bytes.data(), bytes.size());
+            EXPECT(back.sa() == sa.sa());
+            if (n >= 2 && s[0] != s[n - 1]) {
+                std::vector<std::uint8_t> other(s.rbegin(), s.rend());
+                bool threw = false;
+                try {
+                    SuffixArray::load_bytes(other.data(), n, bytes.data(), bytes.size());
+                } catch (const std::runtime_error&) { threw = true; }
+                EXPECT(threw || other == s);
+            }
         }
         // search_all_correctness / contains_correctness vs the naive scan (src/tests.rs:104-121)
         const std::size_t m = n ? rng() % std::min<std::size_t>(n, 12) : 0;

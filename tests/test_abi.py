@@ -27,7 +27,7 @@ def test_header_symbols_exported():
         _lib.build()
     L = ctypes.CDLL(_lib.LIB_PATH)
     names = _declared_symbols()
-    assert len(names) >= 28
+    assert len(names) >= 31
     for name in names:
         assert hasattr(L, name), "libsab200.so does not export %s" % name
     L.sab200_version.restype = ctypes.c_char_p
