@@ -2,9 +2,10 @@
 //
 //   radix_hist_kernel   one sweep over the keys -> 256-bin histograms of every digit place
 //   radix_scan_kernel   exclusive scans of those histograms + "this pass is a no-op" flags
-//   onesweep_kernel     one stable partition pass: keys staged through shared memory, ranked with
-//                       warp-level match_any, tile prefixes chained by decoupled look-back
-//                       (one look-back lane per bin), coalesced write-out from shared memory.
+//   onesweep_kernel     one stable partition pass: tile histogram published early, records ranked per
+//                       warp with ballots, tile prefixes chained by a two-level decoupled look-back
+//                       (one lane per bin; tile partials + group words), records staged in sorted
+//                       order through shared memory, coalesced write-out.
 //
 // Algorithmic traffic: histogram K*m bytes; each pass 2*(K+V)*m bytes.
 // Nothing here is a dense contraction; the bound is HBM bandwidth, tensor cores are not used.
@@ -113,10 +114,9 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
 #ifndef SAB_HW_MATCH_EVERY
 #define SAB_HW_MATCH_EVERY 0
 #endif
-// SAB_MATCH_SMEM = 1: peers through a per-warp shared-memory mask table (atomicOr, read back, leader
-// clears) instead of the eight ballots
-#ifndef SAB_MATCH_SMEM
-#define SAB_MATCH_SMEM 0
+// tiles per look-back group (two-level status words); 0 = single-level look-back over tiles
+#ifndef SAB_LB_GROUP
+#define SAB_LB_GROUP 8
 #endif
 #ifndef SAB_LB_DEPTH
 #define SAB_LB_DEPTH 4
@@ -144,8 +144,7 @@ struct OnesweepCfg {
     static constexpr size_t KEY_BYTES = (size_t)TILE * sizeof(KeyT);
     static constexpr size_t VAL_BYTES = HAS_VAL ? (size_t)TILE * sizeof(u32) : 0;
     static constexpr size_t WHIST_BYTES = (size_t)WARPS * SAB_RADIX_BINS * sizeof(u32);
-    static constexpr size_t MATCH_BYTES = SAB_MATCH_SMEM ? WHIST_BYTES : 0;
-    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + MATCH_BYTES + SAB_RADIX_BINS * sizeof(u32);
+    static constexpr size_t SMEM = KEY_BYTES + VAL_BYTES + WHIST_BYTES + SAB_RADIX_BINS * sizeof(u32);
 };
 
 // Digit extractors.  The padding key of a partial tile (all ones) must map to the last bin in use.
@@ -266,7 +265,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         s_pv[tid] = po.v[tid];
     }
     if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    for (int i = tid; i < (SAB_MATCH_SMEM ? 2 : 1) * WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
+    for (int i = tid; i < WARPS * SAB_RADIX_BINS; i += THREADS) s_whist[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
     const u64 tile_base = (u64)tile * TILE;
@@ -332,40 +331,20 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         }
     }
 
-    // ---- rank inside the warp (stable in (k, lane) order)
+    // ---- tile histogram first (plain shared-memory atomics, order irrelevant), so the tile's partial is
+    // published a whole ranking phase before its successors look back: they never find it missing.
     u32* wh = s_whist + w * SAB_RADIX_BINS;
-    u32* mm = s_whist + (WARPS + w) * SAB_RADIX_BINS;  // mask table of this warp (SAB_MATCH_SMEM only)
-    (void)mm;
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 d = dop(keys[k]);
-#if SAB_MATCH_SMEM
-        atomicOr(&mm[d], 1u << lane);
-        __syncwarp();
-        const u32 peers = mm[d];
-        __syncwarp();
-        if ((peers & lanemask_lt()) == 0) mm[d] = 0;  // the leader resets the slot for the next item
-        __syncwarp();
-#else
-        const u32 peers = (SAB_HW_MATCH_EVERY > 0 && (k % (SAB_HW_MATCH_EVERY > 0 ? SAB_HW_MATCH_EVERY : 1)) == 0)
-                              ? __match_any_sync(SAB_FULL, d)
-                              : match_digit(d);
-#endif
-        const u32 leader = (u32)(__ffs((int)peers) - 1);
-        // The leader's shared-memory atomic returns the running count of this digit in the warp.
-        // Atomics of one warp on one address retire in program order, so item k+1 sees item k's
-        // update; the iterations carry no other dependency and overlap in flight.
-        u32 old = 0;
-        if (lane == leader) old = atomicAdd(&wh[d], (u32)__popc(peers));
-        old = __shfl_sync(SAB_FULL, old, (int)leader);
-        ranks[k] = old + (u32)__popc(peers & lanemask_lt());
-    }
+    for (int k = 0; k < ITEMS; ++k) atomicAdd(&wh[dop(keys[k])], 1u);
     __syncthreads();
-
-    // ---- per bin: exclusive offsets of the warps, tile count; publish the partial
     u32 my_count = 0;
     u64* lb = lookback + (u64)tile * SAB_RADIX_BINS + tid;
     const u64 etag = (u64)epoch << SAB_LB_EPOCH_SHIFT;
+#if SAB_LB_GROUP
+    const u32 grp = tile / SAB_LB_GROUP, gr = tile % SAB_LB_GROUP;
+    // group status words live behind the tile status words of this launch
+    u64* lb2 = lookback + ((n + (u64)TILE - 1) / (u64)TILE + grp) * SAB_RADIX_BINS + tid;
+#endif
     if (tid < SAB_RADIX_BINS) {
         u32 run = 0;
 #pragma unroll
@@ -375,9 +354,36 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             run += c;
         }
         my_count = run;
+#if SAB_LB_GROUP
+        // Two-level status: tile partials (never upgraded) + one word per group of SAB_LB_GROUP tiles, owned by
+        // the group's last tile: PARTIAL = sum of the group's tile counts (published here, early), later
+        // INCLUSIVE = prefix through the end of the group.  A look-back is then the tile's in-group
+        // predecessors (one batch of independent loads) plus a walk over GROUPS, 8x shorter than over tiles.
+        st_relaxed_u64(lb, etag | SAB_LB_FLAG_PARTIAL | (u64)my_count);
+        if (gr == SAB_LB_GROUP - 1) {
+            u64 agg = 0;
+            bool ok;
+            do {
+                u64 v[SAB_LB_GROUP - 1];
+#pragma unroll
+                for (int j = 0; j < SAB_LB_GROUP - 1; ++j) v[j] = ld_relaxed_u64(lb - (u64)(j + 1) * SAB_RADIX_BINS);
+                ok = true;
+                agg = 0;
+#pragma unroll
+                for (int j = 0; j < SAB_LB_GROUP - 1; ++j) {
+                    ok = ok && (v[j] >> SAB_LB_EPOCH_SHIFT) == (u64)epoch && (v[j] & SAB_LB_FLAG_MASK) != 0;
+                    agg += v[j] & SAB_LB_VALUE_MASK;
+                }
+                if (!ok) SAB_SPIN_PAUSE();
+            } while (!ok);
+            st_relaxed_u64(lb2, etag | (grp == 0 ? SAB_LB_FLAG_INCLUSIVE : SAB_LB_FLAG_PARTIAL) | (agg + (u64)my_count));
+        }
+#else
         st_relaxed_u64(lb, etag | (tile == 0 ? SAB_LB_FLAG_INCLUSIVE : SAB_LB_FLAG_PARTIAL) | (u64)my_count);
+#endif
     }
-    // ---- block-exclusive scan of the 256 bin counts -> local start of every bin in the tile
+    // block-exclusive scan of the 256 bin counts; the bin start is folded into the per-warp offsets, so
+    // the ranking atomics below return final shared-memory slots
     u32 my_start = 0;
     {
         u32 incl = warp_incl_sum(my_count);
@@ -387,11 +393,83 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
             u32 woff = 0;
             for (u32 i = 0; i < w; ++i) woff += s_wsum[i];
             my_start = woff + incl - my_count;
-            // fold the bin start into the per-warp offsets: one table lookup per record in the scatter
 #pragma unroll
             for (int ww = 0; ww < WARPS; ++ww) s_whist[ww * SAB_RADIX_BINS + tid] += my_start;
         }
     }
+    __syncthreads();
+    // ---- rank inside the warp (stable in (k, lane) order); ranks[k] = slot of the record in the sorted tile
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 d = dop(keys[k]);
+        const u32 peers = (SAB_HW_MATCH_EVERY > 0 && (k % (SAB_HW_MATCH_EVERY > 0 ? SAB_HW_MATCH_EVERY : 1)) == 0)
+                              ? __match_any_sync(SAB_FULL, d)
+                              : match_digit(d);
+        const u32 leader = (u32)(__ffs((int)peers) - 1);
+        // Atomics of one warp on one address retire in program order, so item k+1 sees item k's update.
+        u32 old = 0;
+        if (lane == leader) old = atomicAdd(&wh[d], (u32)__popc(peers));
+        old = __shfl_sync(SAB_FULL, old, (int)leader);
+        ranks[k] = old + (u32)__popc(peers & lanemask_lt());
+    }
+#if SAB_LB_GROUP
+    // ---- two-level look-back, one lane per bin: in-group tile partials and the first batch of group words
+    // are requested together, so the common case is a single L2 round trip
+    if (tid < SAB_RADIX_BINS) {
+        u64 excl = 0;
+        if (tile > 0) {
+            u64 v1[SAB_LB_GROUP - 1];
+#pragma unroll
+            for (int j = 0; j < SAB_LB_GROUP - 1; ++j)
+                v1[j] = ((u32)j < gr) ? ld_relaxed_u64(lb - (u64)(j + 1) * SAB_RADIX_BINS) : 0ull;
+            i64 t = (i64)grp - 1;
+            bool done = grp == 0;
+            const u64* g0 = lb2 - (u64)grp * SAB_RADIX_BINS;  // word of group 0, this bin
+            u64 v2[SAB_LB_DEPTH];
+#pragma unroll
+            for (int j = 0; j < SAB_LB_DEPTH; ++j) v2[j] = (t - j >= 0) ? ld_relaxed_u64(g0 + (u64)(t - j) * SAB_RADIX_BINS) : 0ull;
+            for (;;) {
+                bool ok = true;
+                u64 sum = 0;
+#pragma unroll
+                for (int j = 0; j < SAB_LB_GROUP - 1; ++j) {
+                    if ((u32)j < gr) {
+                        ok = ok && (v1[j] >> SAB_LB_EPOCH_SHIFT) == (u64)epoch && (v1[j] & SAB_LB_FLAG_MASK) != 0;
+                        sum += v1[j] & SAB_LB_VALUE_MASK;
+                    }
+                }
+                if (ok) {
+                    excl = sum;
+                    break;
+                }
+                SAB_SPIN_PAUSE();
+#pragma unroll
+                for (int j = 0; j < SAB_LB_GROUP - 1; ++j)
+                    v1[j] = ((u32)j < gr) ? ld_relaxed_u64(lb - (u64)(j + 1) * SAB_RADIX_BINS) : 0ull;
+            }
+            while (!done) {
+#pragma unroll
+                for (int j = 0; j < SAB_LB_DEPTH; ++j) {
+                    if (done) break;
+                    const u64 f = v2[j] & SAB_LB_FLAG_MASK;
+                    if ((v2[j] >> SAB_LB_EPOCH_SHIFT) != (u64)epoch || f == 0) break;  // not published yet: reload from here
+                    excl += v2[j] & SAB_LB_VALUE_MASK;
+                    --t;
+                    if (f == SAB_LB_FLAG_INCLUSIVE) done = true;
+                }
+                if (!done) {
+                    SAB_SPIN_PAUSE();
+#pragma unroll
+                    for (int j = 0; j < SAB_LB_DEPTH; ++j)
+                        v2[j] = (t - j >= 0) ? ld_relaxed_u64(g0 + (u64)(t - j) * SAB_RADIX_BINS) : 0ull;
+                }
+            }
+            if (gr == SAB_LB_GROUP - 1 && grp > 0) st_relaxed_u64(lb2, etag | SAB_LB_FLAG_INCLUSIVE | (excl + (u64)my_count));
+        }
+        s_goff[tid] = (u32)(gbase[tid] + excl) - my_start;
+    }
+    __syncthreads();
+#else
     // ---- decoupled look-back, one lane per bin
     if (tid < SAB_RADIX_BINS) {
         u64 excl = 0;
@@ -423,11 +501,11 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     }
     __syncthreads();
 
+#endif
     // ---- scatter into shared memory in sorted order
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const u32 d = dop(keys[k]);
-        const u32 pos = s_whist[w * SAB_RADIX_BINS + d] + ranks[k];
+        const u32 pos = ranks[k];
         s_keys[pos] = keys[k];
         if (HAS_VAL) s_vals[pos] = vals[k];
     }

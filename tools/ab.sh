@@ -1,6 +1,6 @@
 #!/bin/bash
 # developer tool: A/B the variant builds of libsab200 on one box (bench at 256 MiB, device-resident)
-for v in "" _lb1 _lb4 _ms _v5; do
+for v in "" ${AB_VARIANTS:-_lb1 _lb4 _ms _v5}; do
   lib=suffix_array_b200/libsab200$v.so
   [ -f $lib ] || continue
   echo -n "variant '$v': "
