@@ -291,3 +291,36 @@ void launch(dim3 grid, dim3 block, size_t dyn_bytes, const std::function<void()>
 }
 
 }  // namespace emu
+
+// ---- guarded device allocations ---------------------------------------------------------------
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
+#include <mutex>
+namespace {
+std::mutex g_alloc_mu;
+std::map<void*, std::pair<void*, size_t>> g_allocs;  // user pointer -> (mapping base, mapping bytes)
+}  // namespace
+
+void* emu_device_alloc(size_t n) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const size_t body = (n + page - 1) / page * page;
+    const size_t total = body + 2 * page;
+    char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (char*)MAP_FAILED) return nullptr;
+    mprotect(base, page, PROT_NONE);
+    mprotect(base + page + body, page, PROT_NONE);
+    char* user = base + page + ((body - n) & ~(size_t)255);  // 256-byte aligned like cudaMalloc
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    g_allocs[user] = {base, total};
+    return user;
+}
+
+void emu_device_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_allocs.find(p);
+    if (it == g_allocs.end()) return;
+    munmap(it->second.first, it->second.second);
+    g_allocs.erase(it);
+}

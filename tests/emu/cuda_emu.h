@@ -225,14 +225,18 @@ struct cudaDeviceProp {
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : (e == 2 ? "out of memory (emu)" : "error (emu)"); }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+// device allocations end (within 256 B) at an inaccessible guard page: an out-of-bounds kernel access faults
+// here like "illegal memory access" on the GPU instead of silently landing in a neighbouring malloc block
+void* emu_device_alloc(size_t n);
+void emu_device_free(void* p);
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
-    *p = malloc(n ? n : 1);
+    *p = emu_device_alloc(n ? n : 1);
     if (*p) memset(*p, 0xCD, n);  // poison: device memory is not zero-initialised
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template <typename T>
 static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { emu_device_free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <typename T>
 static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
