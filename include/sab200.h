@@ -57,6 +57,9 @@ typedef struct sab200_stats {
     double total_ms;
     double h2d_ms, d2h_ms;
     uint64_t kernel_launches;
+    double group_sort_ms;          /* in-group sorts of the rounds (group_sort_kernel + scatter-back) */
+    uint64_t group_sort_records;   /* records that went through group_sort_kernel */
+    uint64_t group_big_records;    /* ... of which in groups too large for it (radix-sorted) */
 } sab200_stats;
 
 /* ---- construction -------------------------------------------------------------------------

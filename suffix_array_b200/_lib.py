@@ -41,6 +41,9 @@ class Stats(C.Structure):
         ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
+        ("group_sort_ms", C.c_double),
+        ("group_sort_records", C.c_uint64),
+        ("group_big_records", C.c_uint64),
     ]
 
     def as_dict(self):

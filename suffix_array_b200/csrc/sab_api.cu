@@ -197,6 +197,7 @@ void sab_prof_collect(SabContext* c) {
             case 2: c->stats.pack_ms += ms; break;
             case 3: c->stats.rank_ms += ms; break;
             case 4: c->stats.gather_ms += ms; break;
+            case 5: c->stats.group_sort_ms += ms; break;
         }
         c->event_pool.push_back(p.a);
         c->event_pool.push_back(p.b);

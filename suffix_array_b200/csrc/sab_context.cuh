@@ -32,11 +32,14 @@ struct SabStats {
     double total_ms;              // whole device pipeline (events around it)
     double h2d_ms, d2h_ms;        // host entry only
     u64 kernel_launches;          // all kernels launched by the last call
+    double group_sort_ms;         // in-group sorts of the rounds (group_sort_kernel + scatter-back)
+    u64 group_sort_records;       // records that went through group_sort_kernel
+    u64 group_big_records;        // ... of which in groups too large for it (radix-sorted)
 };
 
 struct SabEventPair {
     cudaEvent_t a, b;
-    int kind;  // 0 radix pass, 1 hist, 2 pack, 3 rank, 4 gather
+    int kind;  // 0 radix pass, 1 hist, 2 pack, 3 rank, 4 gather, 5 group sort
 };
 
 struct SabContext {

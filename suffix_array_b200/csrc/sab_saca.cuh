@@ -24,12 +24,18 @@
 #include "sab_context.cuh"
 #include "sab_sort.cuh"
 #include "sab_scan_kernels.cuh"
+#include "sab_group_sort.cuh"
 
 #define SAB_RANK_EMPTY 0xffffffffu
 #ifndef SAB_TEXT_KEYS
 #define SAB_TEXT_KEYS 0
 #endif
 #define SAB_PAD(o) ((o) + ((o) >> 5))  // shared-memory padding, one word per 32; NB: evaluates its argument twice
+// 1: the records of a round are ordered inside their groups by sab_group_sort (one sweep + a radix sort
+// of the large groups only) instead of a radix sort of every record
+#ifndef SAB_GROUP_SORT
+#define SAB_GROUP_SORT 1
+#endif
 #ifdef SAB_EMU
 #ifndef SAB_FILTER_MIN
 #define SAB_FILTER_MIN ((u64)3000)
@@ -441,11 +447,13 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     z.k = k;
     z.dir_shift = dir_shift;
     SortBuffers<u64> rb;  // buffers of the rounds
+    u64 key_cap;          // records each of rb.k[0], rb.k[1] can hold
     if (m <= n / 4) {
         // keep the sorted keys; the composite keys of the rounds ping-pong inside the other key buffer
         z.sorted_keys = sortedK;
         rb.k[0] = free_keys;
         rb.k[1] = free_keys + sab_align_up((size_t)(n + 8) / 2, 32);
+        key_cap = (n + 8) - sab_align_up((size_t)(n + 8) / 2, 32);
         rb.v[0] = act_idx;
         rb.v[1] = buf.v[buf.cur];
         rb.cur = 0;
@@ -458,6 +466,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
         S.kernel_launches++;
         rb.k[0] = buf.k[buf.cur ^ 1];
         rb.k[1] = buf.k[buf.cur];
+        key_cap = n + 8;
         rb.v[0] = act_idx;
         rb.v[1] = buf.v[buf.cur];
         rb.cur = 0;
@@ -469,6 +478,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     const int rank_bits = sab_ceil_log2_u64(n + 2);
     // the split filter (5c) pays off while few groups split: repetitive texts, early rounds
     bool filter_on = (z.sorted_keys == nullptr) && m >= SAB_FILTER_MIN;
+    bool group_sort_on = SAB_GROUP_SORT != 0;
     while (m > 0) {
         ++round;
         if (round >= SAB_MAX_ROUNDS || h > n) {
@@ -511,7 +521,28 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             sb.v[0] = rb.v[rb.cur];
             sb.v[1] = rb.v[rb.cur ^ 1] + n_stay;
             sb.cur = 0;
-            SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+            // 5d. small groups are ordered in one sweep; the spare buffers for the records of big groups are
+            // the unused tails of the round buffers (keys, payloads) and of r1buf (positions)
+            int sorted = 0;
+            if (group_sort_on) {
+                const u64 used = sab_align_up(n_sort, 64);
+                const u64 cap_keys = key_cap > used ? key_cap - used : 0;
+                const u64 cap_vals = n + 8 > n_stay + used ? n + 8 - n_stay - used : 0;
+                GroupSortSpare sp;
+                sp.k[0] = sb.k[0] + used;
+                sp.k[1] = sb.k[1] + used;
+                sp.v[0] = sb.v[0] + used;
+                sp.v[1] = sb.v[1] + used;
+                sp.pos = r1buf + n_stay;
+                sp.cap = cap_keys < cap_vals ? cap_keys : cap_vals;
+                if (sp.cap * 8 >= n_sort) {
+                    u64 nbig = 0;
+                    sorted = sab_group_sort(c, sb, n_sort, 32 + rank_bits, sp, &S.passes[round], &nbig);
+                    if (sorted < 0) return sorted;
+                    if (nbig * 2 > n_sort) group_sort_on = false;  // mostly large groups: the sweep does not pay
+                }
+            }
+            if (!sorted) SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
             u32* out_idx = (sb.cur == 0) ? rb.v[rb.cur ^ 1] + n_stay : rb.v[rb.cur];
             {
                 const u64 tiles = div_up64(n_sort, SAB_SCAN_TILE);
