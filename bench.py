@@ -280,7 +280,8 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "MB/s", "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": n,
                     "d2h_bytes_per_step": 4 * (n + 1), "api": "sab200_saca (host buffers, pinned)"},
             "cpu_baseline": cpu, "gpu_launches": int(launches), "search": search,
-            "breakdown_ms": {k: round(stats[k], 3) for k in ("total_ms", "radix_pass_ms", "hist_ms", "pack_ms", "rank_ms", "gather_ms")},
+            "breakdown_ms": {k: round(stats[k], 3) for k in ("total_ms", "radix_pass_ms", "hist_ms", "pack_ms", "rank_ms", "gather_ms", "group_sort_ms")},
+            "group_sort": {"records": stats["group_sort_records"], "in_large_groups": stats["group_big_records"]},
             "clocks": sampler.summary()}))
     if world > 1:
         dist.destroy_process_group()

@@ -68,9 +68,7 @@ void sab_context_destroy(SabContext* c) {
     cudaFreeHost(c->h_small);
     cudaFree(c->d_lookback);
     cudaFree(c->d_ticket);
-    cudaFree(c->d_scan_flags);
-    cudaFree(c->d_scan_partial);
-    cudaFree(c->d_scan_inclusive);
+    cudaFree(c->d_scan_slots);
     cudaFree(c->d_counters);
     cudaFree(c->arena);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -143,19 +141,15 @@ int sab_ensure_lookback(SabContext* c, size_t tiles) {
 
 int sab_ensure_scan(SabContext* c, size_t tiles) {
     if (c->scan_tiles >= tiles) return SAB_OK;
-    if (c->d_scan_flags) {
+    if (c->d_scan_slots) {
         SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_scan_flags);
-        cudaFree(c->d_scan_partial);
-        cudaFree(c->d_scan_inclusive);
-        c->d_scan_flags = c->d_scan_partial = c->d_scan_inclusive = nullptr;
+        cudaFree(c->d_scan_slots);
+        c->d_scan_slots = nullptr;
         c->scan_tiles = 0;
     }
     const size_t want = tiles + tiles / 8 + 64;
-    SAB_CUDA_TRY(cudaMalloc(&c->d_scan_flags, want * sizeof(u32)));
-    SAB_CUDA_TRY(cudaMalloc(&c->d_scan_partial, want * 16));
-    SAB_CUDA_TRY(cudaMalloc(&c->d_scan_inclusive, want * 16));
-    SAB_CUDA_TRY(cudaMemsetAsync(c->d_scan_flags, 0, want * sizeof(u32), c->stream));
+    SAB_CUDA_TRY(cudaMalloc(&c->d_scan_slots, want * sizeof(ScanSlot)));
+    SAB_CUDA_TRY(cudaMemsetAsync(c->d_scan_slots, 0, want * sizeof(ScanSlot), c->stream));
     c->scan_tiles = want;
     c->scan_epoch = 0;
     return SAB_OK;

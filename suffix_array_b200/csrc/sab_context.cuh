@@ -58,9 +58,7 @@ struct SabContext {
     u32 ticket_host = 0;
     u32 lb_epoch = 0;
     // chained-scan scratch (3 x u32 states at most)
-    u32* d_scan_flags = nullptr;
-    u32* d_scan_partial = nullptr;
-    u32* d_scan_inclusive = nullptr;
+    ScanSlot* d_scan_slots = nullptr;  // chained-scan status, one 16-byte slot per tile
     size_t scan_tiles = 0;
     u32 scan_epoch = 0;
     u32* d_counters = nullptr;  // [16] device scalars
@@ -101,10 +99,11 @@ template <typename T>
 static inline TileState<T> sab_tile_state(SabContext* c, size_t tiles) {
     (void)tiles;
     TileState<T> st;
-    st.flags = c->d_scan_flags;
-    st.partial = (T*)c->d_scan_partial;
-    st.inclusive = (T*)c->d_scan_inclusive;
-    if (++c->scan_epoch >= (1u << 30)) c->scan_epoch = 1;  // wrap: flags are re-zeroed by sab_ensure_scan
+    st.slots = c->d_scan_slots;
+    if (++c->scan_epoch >= (1u << 30)) {  // wrap: stale tags of 2^30 launches ago must not match
+        cudaMemsetAsync(c->d_scan_slots, 0, c->scan_tiles * sizeof(ScanSlot), c->stream);
+        c->scan_epoch = 1;
+    }
     st.epoch = c->scan_epoch;
     return st;
 }

@@ -2,20 +2,74 @@
 // POD states.  Each tile publishes its aggregate (PARTIAL) as soon as it is known and its
 // inclusive prefix once the look-back has resolved; a warp inspects 32 predecessors per step.
 //
-// The flag words carry a launch epoch so the status arrays never need clearing between launches:
-// a word whose epoch differs from the current launch's reads as EMPTY.
+// The slot tags carry a launch epoch so the status array never needs clearing between launches:
+// a slot whose epoch differs from the current launch's reads as EMPTY.
 #pragma once
 #include "sab_common.cuh"
 
 enum : u32 { SCAN_EMPTY = 0u, SCAN_PARTIAL = 1u, SCAN_INCLUSIVE = 2u };
 
+// One status slot per tile: the state tag and the value travel in ONE aligned 16-byte access, so a
+// look-back step costs a single L2 round trip and needs no fence between "flag" and "value"
+// (16-byte accesses of one thread to an aligned address are performed as one transaction).
+struct alignas(16) ScanSlot {
+    u32 tag;   // (epoch << 2) | state
+    u32 w[3];  // the POD value (at most 12 bytes)
+};
+
 template <typename T>
 struct TileState {
-    u32* flags;    // [tiles]   (epoch << 2) | state
-    T* partial;    // [tiles]
-    T* inclusive;  // [tiles]
-    u32 epoch;     // 1 .. 2^30-1, unique per launch
+    ScanSlot* slots;  // [tiles]
+    u32 epoch;        // 1 .. 2^30-1, unique per launch
 };
+
+__device__ __forceinline__ ScanSlot ld_slot(const ScanSlot* p) {
+    ScanSlot s;
+#ifdef SAB_EMU
+    memcpy(&s, p, sizeof(s));  // fibers switch only at explicit yield points
+#else
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(s.tag), "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2])
+                 : "l"(p)
+                 : "memory");
+#endif
+    return s;
+}
+__device__ __forceinline__ void st_slot(ScanSlot* p, const ScanSlot& s) {
+#ifdef SAB_EMU
+    memcpy(p, &s, sizeof(s));
+#else
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(s.tag), "r"(s.w[0]), "r"(s.w[1]), "r"(s.w[2])
+                 : "memory");
+#endif
+}
+template <typename T>
+__device__ __forceinline__ ScanSlot make_slot(u32 tag, const T& v) {
+    static_assert(sizeof(T) % 4 == 0 && sizeof(T) <= 12, "POD scan state: 4, 8 or 12 bytes");
+    union {
+        T t;
+        u32 w[3];
+    } u;
+    u.w[0] = u.w[1] = u.w[2] = 0;
+    u.t = v;
+    ScanSlot s;
+    s.tag = tag;
+    s.w[0] = u.w[0];
+    s.w[1] = u.w[1];
+    s.w[2] = u.w[2];
+    return s;
+}
+template <typename T>
+__device__ __forceinline__ T slot_value(const ScanSlot& s) {
+    union {
+        T t;
+        u32 w[3];
+    } u;
+    u.w[0] = s.w[0];
+    u.w[1] = s.w[1];
+    u.w[2] = s.w[2];
+    return u.t;
+}
 
 template <typename T>
 __device__ __forceinline__ T shfl_xor_pod(T v, int m) {
@@ -58,15 +112,11 @@ __device__ __forceinline__ T tile_exclusive_prefix(const TileState<T>& st, u32 t
         const u32 tag = st.epoch << 2;
         if (tile == 0) {
             if (lane == 0) {
-                st.inclusive[0] = aggregate;
-                st_release_u32(&st.flags[0], tag | SCAN_INCLUSIVE);
+                st_slot(&st.slots[0], make_slot<T>(tag | SCAN_INCLUSIVE, aggregate));
                 s_prefix = identity;
             }
         } else {
-            if (lane == 0) {
-                st.partial[tile] = aggregate;
-                st_release_u32(&st.flags[tile], tag | SCAN_PARTIAL);
-            }
+            if (lane == 0) st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_PARTIAL, aggregate));
             T running = identity;
             i64 base = (i64)tile - 1;
             while (true) {
@@ -75,12 +125,14 @@ __device__ __forceinline__ T tile_exclusive_prefix(const TileState<T>& st, u32 t
                 T val = identity;
                 if (t >= 0) {
                     while (true) {
-                        const u32 wv = ld_acquire_u32(&st.flags[t]);
-                        f = ((wv >> 2) == st.epoch) ? (wv & 3u) : (u32)SCAN_EMPTY;
-                        if (f != SCAN_EMPTY) break;
+                        const ScanSlot s = ld_slot(&st.slots[t]);
+                        f = ((s.tag >> 2) == st.epoch) ? (s.tag & 3u) : (u32)SCAN_EMPTY;
+                        if (f != SCAN_EMPTY) {
+                            val = slot_value<T>(s);
+                            break;
+                        }
                         SAB_SPIN_PAUSE();
                     }
-                    val = (f == SCAN_INCLUSIVE) ? st.inclusive[t] : st.partial[t];
                 }
                 const u32 incl = __ballot_sync(SAB_FULL, f == SCAN_INCLUSIVE);
                 const u32 first = incl ? (u32)(__ffs((int)incl) - 1) : 31u;
@@ -90,8 +142,7 @@ __device__ __forceinline__ T tile_exclusive_prefix(const TileState<T>& st, u32 t
                 base -= 32;
             }
             if (lane == 0) {
-                st.inclusive[tile] = op(running, aggregate);
-                st_release_u32(&st.flags[tile], tag | SCAN_INCLUSIVE);
+                st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_INCLUSIVE, op(running, aggregate)));
                 s_prefix = running;
             }
         }

@@ -18,6 +18,9 @@
 #define SAB_SCAN_WARPS (SAB_SCAN_THREADS / 32)
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_WCHUNK (32 * SAB_SCAN_ITEMS)
+#ifndef SAB_INIT_MIN_BLOCKS
+#define SAB_INIT_MIN_BLOCKS 2
+#endif
 
 __device__ __forceinline__ u32 lanemask_le() { return lanemask_lt() | (1u << lane_id()); }
 __device__ __forceinline__ u32 high_bit(u32 m) { return 31u - (u32)__clz((int)m); }  // m != 0
@@ -89,7 +92,7 @@ struct RankScanOp {
 //   rank != null:     rank[I[j]] = r for those active records only (lazy ISA)
 //   rank_seq != null: rank_seq[j] = r for every record (multi-GPU: ranks travel to the owner of I[j])
 //   dir != null:      dir[key >> dir_shift] = j at the first record of every directory bucket
-__global__ void __launch_bounds__(SAB_SCAN_THREADS)
+__global__ void __launch_bounds__(SAB_SCAN_THREADS, SAB_INIT_MIN_BLOCKS)
 init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u32 rank_base, u32* __restrict__ rank,
                   u32* __restrict__ rank_seq, u32* __restrict__ sa_out, u32* __restrict__ act_r1,
                   u32* __restrict__ act_idx, u32* __restrict__ d_count, u32* __restrict__ dir, int dir_shift,
