@@ -19,7 +19,7 @@
 #define SAB_SCAN_TILE (SAB_SCAN_THREADS * SAB_SCAN_ITEMS)
 #define SAB_WCHUNK (32 * SAB_SCAN_ITEMS)
 #ifndef SAB_INIT_MIN_BLOCKS
-#define SAB_INIT_MIN_BLOCKS 2
+#define SAB_INIT_MIN_BLOCKS 3
 #endif
 
 __device__ __forceinline__ u32 lanemask_le() { return lanemask_lt() | (1u << lane_id()); }
