@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
-                    help="default: c2 on one GPU (BASELINE.json configs[1]), c4 on several (configs[3])")
+                    help="default: c2 (BASELINE.json configs[1]) at every N; c4 = the 3.9 GiB text of configs[3]")
     ap.add_argument("--n-mib", type=int, default=0, help="override the text size (MiB); 0 = the named config")
     ap.add_argument("--ref-sample-mib", type=int, default=16)
     ap.add_argument("--cpu-sample-mib", type=int, default=32)
@@ -161,7 +161,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
-        args.workload = "c2" if world == 1 else "c4"
+        # the same text at every N, so that the driver's 1 -> 8 GPU ratio is a strong-scaling figure of one
+        # workload; the 3.9 GiB text of configs[3] is `--workload c4` (profiles/r01_multi_gpu.md)
+        args.workload = "c2"
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -180,6 +182,9 @@ def main():
     desc, n, _ = WORKLOADS[args.workload]
     if args.n_mib:
         n = args.n_mib << 20
+    if n > (3 << 30):
+        raise SystemExit("the 3.9 GiB text leaves no room for the device-resident AND host-buffer legs on one GPU: "
+                         "run tools/c4_single.py (host-buffer entry, verified by sab200_check)")
     # N > 1: independent replicas, one text per rank (different seed) -- see DESIGN.md "Multi-GPU"
     text = make_text(args.workload, n, seed_shift=rank)
     dev = torch.device("cuda", local_rank)

@@ -19,6 +19,7 @@ collectives are torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tes
 "device" is the SIMT-emulator build).  Tensors are used as untyped device buffers.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -86,6 +87,7 @@ class _Ctx:
         self.a2a_bytes = 0
         self.collectives = 0
         self.phase_ms = {}
+        self.tracing = os.environ.get("SAB_DIST_TRACE", "0") == "1"
         self._t = None
 
     def mark(self, name):
@@ -96,6 +98,12 @@ class _Ctx:
         if self._t is not None:
             self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (now - self._t) * 1e3
         self._t = now
+
+    def trace(self, name):
+        """Sub-phase timer of the doubling rounds; only with SAB_DIST_TRACE=1 (it adds a device sync per mark,
+        so traced runs are for attribution, not for the headline number)."""
+        if self.tracing:
+            self.mark(name)
 
     def check(self, rc, what):
         if rc < 0:
@@ -362,6 +370,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         rounds += 1
         if h > n or rounds > 64:
             raise RuntimeError("prefix doubling did not converge")
+        cx.trace("rounds/count")
         key64 = cx.empty(m, torch.int64)
         p2p_round = use_p2p and tot <= P2P_MAX_RECORDS * P  # same decision on every rank
         if p2p_round:
@@ -371,16 +380,21 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         else:
             # requests i+h to the owners, answers back in the same order
             ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, B)
+            cx.trace("rounds/partition_requests")
             recv = cx.exchange_counts(send)
             q = cx.all_to_all(ipart, send, recv)
+            cx.trace("rounds/send_requests")
             ans = cx.empty(q.numel(), torch.int32)
             cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev)
+            cx.trace("rounds/gather")
             r2 = cx.all_to_all(ans, recv, send)
+            cx.trace("rounds/send_answers")
             cx.call("sab200_dist_make_keys", _p(rpart), _p(r2), m, _p(key64), cx.dev)
         key_tmp = cx.empty(m, torch.int64)
         idx_tmp = cx.empty(m, torch.int32)
         which = cx.call("sab200_dist_sort_pairs", _p(key64), _p(key_tmp), _p(ipart), _p(idx_tmp), m, 32 + rank_bits, cx.dev)
         sk, si = (key64, ipart) if which == 0 else (key_tmp, idx_tmp)
+        cx.trace("rounds/sort")
         out_r1 = cx.empty(m, torch.int32)
         out_idx = cx.empty(m, torch.int32)
         upd_idx = cx.empty(m, torch.int32)
@@ -388,15 +402,17 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         kept = C.c_uint64()
         cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
                 C.byref(kept), cx.dev)
+        cx.trace("rounds/rerank")
         if p2p_round:
             _barrier(cx)  # every rank has finished loading ranks of this round
             cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, B, P, peer_arg, cx.dev)
         else:
             _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
+        cx.trace("rounds/update_ranks")
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
-    cx.mark("rounds")
+    cx.mark("rounds/count" if cx.tracing else "rounds")
     cx.call("sab200_dist_end", cx.dev)
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
