@@ -61,7 +61,16 @@ int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint32_t* d_val
                                     uint32_t B, int32_t P, uint32_t* d_key_out, uint32_t* d_val_out, uint64_t* counts,
                                     int32_t device);
 
-/* d_rank_local[d_pos[t] - lo] = d_val[t]   (ranks arriving at their owner) */
+/* Stable partition of (pos, val) u32 pairs by the rank whose suffix-array slice holds SA position pos:
+ * slice_start (host, P x u32) = first SA position of every rank's slice, ascending; pos equal to
+ * 0xFFFFFFFF is dropped.  Used when the active lists have been rebalanced across the GPUs, so a newly
+ * unique suffix may belong to another rank's slice.  counts (host, P x u64). */
+int32_t sab200_dist_partition_slices(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count,
+                                     const uint32_t* slice_start, int32_t P, uint32_t* d_pos_out, uint32_t* d_val_out,
+                                     uint64_t* counts, int32_t device);
+
+/* d_rank_local[d_pos[t] - lo] = d_val[t]   (ranks arriving at their owner; also SA entries arriving at
+ * the owner of their slice, with lo = the slice offset) */
 int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo,
                             uint32_t* d_rank_local, int32_t device);
 /* d_out[t] = d_rank_local[d_pos[t] + add - lo]   (answering rank[i+h] requests) */
@@ -73,10 +82,13 @@ int32_t sab200_dist_make_keys(const uint32_t* d_r1, const uint32_t* d_r2, uint64
 
 /* One re-ranking step on this rank's sorted active records (see rerank_kernel): newly unique suffixes
  * are written to d_sa_local[rank - sa_off]; the rest is compacted into (d_out_r1, d_out_idx), *n_kept
- * (host); (d_upd_idx[j], d_upd_r[j]) lists every changed rank (0xFFFFFFFF in d_upd_idx = unchanged). */
+ * (host); (d_upd_idx[j], d_upd_r[j]) lists every changed rank (0xFFFFFFFF in d_upd_idx = unchanged).
+ * d_set_pos != NULL (rebalanced active lists): nothing is written to d_sa_local; d_set_pos[j] = SA
+ * position of record j if it became unique, else 0xFFFFFFFF -- the caller routes (d_set_pos, d_idx)
+ * to the owners of the slices (sab200_dist_partition_slices). */
 int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint64_t m, uint32_t sa_off,
                            uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
-                           uint32_t* d_upd_r, uint64_t* n_kept, int32_t device);
+                           uint32_t* d_upd_r, uint32_t* d_set_pos, uint64_t* n_kept, int32_t device);
 
 /* Peer-to-peer form of the round exchanges (NVLink): peer_rank_ptrs (host array of P device addresses)
  * are the rank[] blocks of all GPUs mapped into this process (symmetric memory; block g holds the ranks

@@ -204,6 +204,26 @@ extern "C" int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint
     return SAB_OK;
 }
 
+extern "C" int32_t sab200_dist_partition_slices(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count,
+                                                const uint32_t* slice_start, int32_t P, uint32_t* d_pos_out,
+                                                uint32_t* d_val_out, uint64_t* counts, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (P < 1 || P > SAB_MAX_RANKS || !slice_start || !counts) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SliceDigit dop;
+    for (int i = 0; i < SAB_MAX_RANKS; ++i) dop.start[i] = i < P ? slice_start[i] : 0xffffffffu;
+    dop.pmax = (u32)P - 1;
+    SAB_TRY((sab_count_and_base<u32, SliceDigit>(c, d_pos, count, dop, P, counts)));
+    if (count) {
+        constexpr int TILE = PassShape<u32>::THREADS * PassShape<u32>::ITEMS;
+        SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
+        SAB_TRY((sab_launch_pass_op<u32, false, SliceDigit>(c, d_pos, d_pos_out, d_val, d_val_out, count, dop, c->d_gbase)));
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
 extern "C" int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo,
                                        uint32_t* d_rank_local, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
@@ -245,7 +265,7 @@ extern "C" int32_t sab200_dist_make_keys(const uint32_t* d_r1, const uint32_t* d
 
 extern "C" int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint64_t m, uint32_t sa_off,
                                       uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
-                                      uint32_t* d_upd_r, uint64_t* n_kept, int32_t device) {
+                                      uint32_t* d_upd_r, uint32_t* d_set_pos, uint64_t* n_kept, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
     if (!n_kept) return SAB_ERR_ARGS;
@@ -260,7 +280,7 @@ extern "C" int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d
     // ranks are global SA positions: index the local slice through a pointer shifted by the slice offset
     u32* sa_shifted = d_sa_local - (size_t)sa_off;
     SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, d_key64, d_idx, m, (u32*)nullptr, sa_shifted, d_out_r1,
-               d_out_idx, d_upd_idx, d_upd_r, d_m, ts);
+               d_out_idx, d_upd_idx, d_upd_r, d_set_pos, d_m, ts);
     SAB_LAUNCH_CHECK();
     SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));

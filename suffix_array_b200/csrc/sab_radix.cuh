@@ -173,6 +173,18 @@ struct OwnerDigit {  // owner rank of text position key + add under a block dist
     }
 };
 
+struct SliceDigit {  // rank whose suffix-array slice [start[g], start[g+1]) holds SA position k (multi-GPU)
+    u32 start[SAB_MAX_RANKS];  // start[0] is not compared: everything below start[1] belongs to rank 0
+    u32 pmax;
+    __device__ __forceinline__ u32 operator()(u32 k) const {
+        if (k == 0xffffffffu) return pmax + 1u;  // dropped record / tile padding: behind the last rank
+        u32 d = 0;
+#pragma unroll
+        for (int i = 1; i < SAB_MAX_RANKS; ++i) d += ((u32)i <= pmax && start[i] <= k) ? 1u : 0u;
+        return d;
+    }
+};
+
 // TEXT passes: the keys of the initial sort are never materialised before the first radix pass.  The
 // histogram sweep and the first pass re-derive them from the text: a tile's bytes are staged in shared
 // memory as codes and each thread slides a k-symbol window over ITEMS consecutive positions

@@ -550,7 +550,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
                 sab_prof_begin(c, 3);
                 SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)sb.k[sb.cur],
                            (const u32*)sb.v[sb.cur], n_sort, rank, d_sa, r1buf + n_stay, out_idx, (u32*)nullptr, (u32*)nullptr,
-                           d_m, ts);
+                           (u32*)nullptr, d_m, ts);
                 sab_prof_end(c);
                 SAB_LAUNCH_CHECK();
                 S.kernel_launches++;

@@ -178,12 +178,14 @@ struct RerankScanOp {
 //   changed rank  -> rank[I[j]] = new_r1            (rank != null: single GPU)
 //                    upd_idx[j] = I[j], upd_r[j] = new_r1, or upd_idx[j] = 0xFFFFFFFF when unchanged
 //                    (upd_idx != null: multi-GPU, the owner of rank[I[j]] is another GPU)
-//   singleton     -> sa[new_r1] = I[j] (final), dropped
+//   singleton     -> sa[new_r1] = I[j] (final), dropped; with set_pos != null the store is left to the
+//                    caller instead: set_pos[j] = new_r1 for singletons, 0xFFFFFFFF otherwise (multi-GPU
+//                    with rebalanced active lists: SA position new_r1 may belong to another GPU)
 //   otherwise     -> appended to (out_r1, out_idx)
 __global__ void __launch_bounds__(SAB_SCAN_THREADS, 2)
 rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* __restrict__ rank, u32* __restrict__ sa,
               u32* __restrict__ out_r1, u32* __restrict__ out_idx, u32* __restrict__ upd_idx, u32* __restrict__ upd_r,
-              u32* __restrict__ d_count, TileState<RerankScan> st) {
+              u32* __restrict__ set_pos, u32* __restrict__ d_count, TileState<RerankScan> st) {
     const u32 tile = blockIdx.x, lane = lane_id();
     const u64 base = (u64)tile * SAB_SCAN_TILE;
     const u64 wbase = base + (u64)warp_id() * SAB_WCHUNK;
@@ -241,13 +243,15 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
                 upd_idx[j] = nr != r1 ? idx[k] : 0xffffffffu;
                 upd_r[j] = nr;
             }
-            if ((kb[k] >> lane) & 1u) {
+            const bool keep = (kb[k] >> lane) & 1u;
+            if (keep) {
                 const u32 pos = run.cnt + (u32)__popc(kb[k] & lanemask_lt());
                 out_r1[pos] = nr;
                 out_idx[pos] = idx[k];
-            } else {
+            } else if (!set_pos) {
                 sa[nr] = idx[k];
             }
+            if (set_pos) set_pos[j] = keep ? 0xffffffffu : nr;
         }
         if (ob[k]) run.ogs = (u32)row + high_bit(ob[k]);
         if (nb[k]) run.nhs = (u32)row + high_bit(nb[k]);

@@ -31,7 +31,10 @@ HALO = 64
 # Above this many records per rank an exchange goes through partition + all_to_all (bulk NVLink
 # transfers, local random access); below it the kernels load / store the owners' blocks directly
 # (no collective, but 4-byte remote accesses).  Measured cross-over on 8 B200: a few 10^7 records.
-P2P_MAX_RECORDS = int(__import__("os").environ.get("SAB_P2P_MAX_RECORDS", 16 << 20))
+P2P_MAX_RECORDS = int(os.environ.get("SAB_P2P_MAX_RECORDS", 16 << 20))
+# Active lists are evened out across the ranks (see _rebalance) when they average at least this many records
+# per rank and the longest exceeds the mean by 10 %: below that a round is launch-bound anyway.
+REBALANCE_MIN_RECORDS = int(os.environ.get("SAB_REBALANCE_MIN", 1 << 20))
 
 
 def shard_bounds(n, rank, world):
@@ -60,7 +63,8 @@ def _bind(L):
         "sab200_dist_scatter": [vp, vp, u64, u32, vp, i32],
         "sab200_dist_gather": [vp, u64, u32, u32, vp, vp, i32],
         "sab200_dist_make_keys": [vp, vp, u64, vp, i32],
-        "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
+        "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
+        "sab200_dist_partition_slices": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
         "sab200_dist_begin": [i32],
         "sab200_dist_end": [i32],
         "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, vp, vp, i32],
@@ -205,6 +209,67 @@ def _send_ranks(cx, idx, ranks, count, B, lo, rank_local):
     ri = cx.all_to_all(kp, send, recv)
     rr = cx.all_to_all(vp, send, recv)
     cx.call("sab200_dist_scatter", _p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev)
+
+
+def _next_group_boundary(r1, c, m):
+    """Smallest p >= c that starts a group of the rank-sorted list r1[:m] (p = m if none)."""
+    if c <= 0:
+        return 0
+    if c >= m:
+        return m
+    v = r1[c - 1]
+    p, w = c, 4096
+    while p < m:
+        seg = r1[p:min(m, p + w)]
+        ne = (seg != v).nonzero()
+        if ne.numel():
+            return p + int(ne[0])
+        p += seg.numel()
+        w *= 4
+    return m
+
+
+def _rebalance(cx, act_r1, act_idx, m):
+    """Evens out the active lists.  The suffix-array slices hold equal numbers of SUFFIXES, not of active
+    ones (on the mixed text the English-like key ranges hold nearly all of them), and every round costs
+    what its longest list costs.  The lists are globally sorted by rank and groups never straddle ranks,
+    so moving cut points to group boundaries and shipping contiguous chunks keeps both properties.
+    Returns (r1, idx, m, moved)."""
+    P, rank = cx.P, cx.rank
+    mine = torch.tensor([m], dtype=torch.int64, device=cx.device)
+    allm = [torch.empty_like(mine) for _ in range(P)]
+    dist.all_gather(allm, mine, group=cx.group)
+    cx.collectives += 1
+    ms = [int(x.item()) for x in allm]
+    M = sum(ms)
+    if M < REBALANCE_MIN_RECORDS * P or max(ms) * P <= 1.1 * M:
+        return act_r1[:m], act_idx[:m], m, False
+    Q = -(-M // P)
+    off = sum(ms[:rank])
+    bounds = [0]
+    for j in range(1, P):
+        c = min(max(j * Q - off, 0), m)
+        bounds.append(max(bounds[-1], _next_group_boundary(act_r1, c, m)))
+    bounds.append(m)
+    send = [bounds[j + 1] - bounds[j] for j in range(P)]
+    recv = cx.exchange_counts(send)
+    r1 = cx.all_to_all(act_r1[:m], send, recv)
+    idx = cx.all_to_all(act_idx[:m], send, recv)
+    return r1, idx, r1.numel(), True
+
+
+def _send_sa(cx, pos, idx, count, starts, sa_off, sa_local):
+    """sa[pos[t]] = idx[t] on the GPU whose slice holds SA position pos[t] (entries with pos = 0xFFFFFFFF are dropped)."""
+    kp = cx.empty(count, torch.int32)
+    vp = cx.empty(count, torch.int32)
+    cnt = np.zeros(cx.P, dtype=np.uint64)
+    cx.call("sab200_dist_partition_slices", _p(pos), _p(idx), count, starts.ctypes.data_as(C.c_void_p), cx.P, _p(kp), _p(vp),
+            cnt.ctypes.data_as(C.c_void_p), cx.dev)
+    send = [int(x) for x in cnt]
+    recv = cx.exchange_counts(send)
+    rp = cx.all_to_all(kp, send, recv)
+    ri = cx.all_to_all(vp, send, recv)
+    cx.call("sab200_dist_scatter", _p(rp), _p(ri), rp.numel(), sa_off, _p(sa_local), cx.dev)
 
 
 def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
@@ -356,7 +421,9 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     cx.mark("ranks_to_owners")
     # 6. doubling rounds
     rank_bits = max(1, int(n + 1).bit_length())
-    cur_r1, cur_idx = act_r1[:m], act_idx[:m]
+    cur_r1, cur_idx, m, rebalanced = _rebalance(cx, act_r1, act_idx, m)
+    starts = np.array([1 + sum(sizes[:g]) for g in range(P)], dtype=np.uint32)  # first SA position of every slice
+    cx.mark("rebalance")
     h = k
     rounds = 0
     active = []
@@ -400,8 +467,9 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         upd_idx = cx.empty(m, torch.int32)
         upd_r = cx.empty(m, torch.int32)
         kept = C.c_uint64()
+        set_pos = cx.empty(m, torch.int32) if rebalanced else None
         cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
-                C.byref(kept), cx.dev)
+                _p(set_pos) if rebalanced else None, C.byref(kept), cx.dev)
         cx.trace("rounds/rerank")
         if p2p_round:
             _barrier(cx)  # every rank has finished loading ranks of this round
@@ -409,6 +477,9 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         else:
             _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
         cx.trace("rounds/update_ranks")
+        if rebalanced:
+            _send_sa(cx, set_pos, si, m, starts, sa_off, sa_local)
+            cx.trace("rounds/route_sa")
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
@@ -417,7 +488,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
-                      "exchange": "p2p" if use_p2p else "collective",
+                      "exchange": "p2p" if use_p2p else "collective", "rebalanced": rebalanced,
                       "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()},
                       "wall_ms": round((time.perf_counter() - t_enter) * 1e3, 2)})
     return sa_local, sa_off
