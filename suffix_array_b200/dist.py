@@ -422,6 +422,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     # 6. doubling rounds
     rank_bits = max(1, int(n + 1).bit_length())
     cur_r1, cur_idx, m, rebalanced = _rebalance(cx, act_r1, act_idx, m)
+    del act_r1, act_idx  # views (not moved) keep the storage alive; moved lists replace it
     starts = np.array([1 + sum(sizes[:g]) for g in range(P)], dtype=np.uint32)  # first SA position of every slice
     cx.mark("rebalance")
     h = k
@@ -471,15 +472,22 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         cx.call("sab200_dist_rerank", _p(sk), _p(si), m, sa_off, _p(sa_local), _p(out_r1), _p(out_idx), _p(upd_idx), _p(upd_r),
                 _p(set_pos) if rebalanced else None, C.byref(kept), cx.dev)
         cx.trace("rounds/rerank")
+        # free what the round no longer needs before the exchanges allocate their buffers (the 3.9 GiB text on
+        # 2 GPUs runs within a few GB of the device memory)
+        del sk, key64, key_tmp
+        if not p2p_round:
+            del q, ans, r2, rpart
+        if rebalanced:
+            _send_sa(cx, set_pos, si, m, starts, sa_off, sa_local)
+            cx.trace("rounds/route_sa")
+        del set_pos, si, ipart, idx_tmp, cur_r1, cur_idx
         if p2p_round:
             _barrier(cx)  # every rank has finished loading ranks of this round
             cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, B, P, peer_arg, cx.dev)
         else:
             _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
+        del upd_idx, upd_r
         cx.trace("rounds/update_ranks")
-        if rebalanced:
-            _send_sa(cx, set_pos, si, m, starts, sa_off, sa_local)
-            cx.trace("rounds/route_sa")
         m = kept.value
         cur_r1, cur_idx = out_r1[:m], out_idx[:m]
         h *= 2
