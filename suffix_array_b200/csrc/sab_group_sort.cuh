@@ -71,13 +71,18 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
         if (p < valid) {
             const u64 key = s_key[p + 1];
             const u32 r1 = (u32)(key >> 32);
+            // groups are contiguous: an equal r1 at distance SAB_GSORT_MAX settles "large" with one read, so the
+            // neighbour scans below only ever walk over small groups
+            if (p >= SAB_GSORT_MAX && (u32)(s_key[p + 1 - SAB_GSORT_MAX] >> 32) == r1) big = true;
+            if (p + SAB_GSORT_MAX < valid && (u32)(s_key[p + 1 + SAB_GSORT_MAX] >> 32) == r1) big = true;
             // a = first record of the group (or the scan limit), b = one past its last record
-            u32 a = p;
-            while (a > 0 && p - a < SAB_GSORT_MAX && (u32)(s_key[a] >> 32) == r1) --a;
-            if ((u32)(s_key[a] >> 32) == r1) big = true;  // runs into the previous tile, or longer than the limit
-            u32 b = p + 1;
-            while (b < valid && b - a <= SAB_GSORT_MAX && (u32)(s_key[b + 1] >> 32) == r1) ++b;
-            if (b - a > SAB_GSORT_MAX || (b == valid && (u32)(s_key[valid + 1] >> 32) == r1)) big = true;
+            u32 a = p, b = p + 1;
+            if (!big) {
+                while (a > 0 && p - a < SAB_GSORT_MAX && (u32)(s_key[a] >> 32) == r1) --a;
+                if ((u32)(s_key[a] >> 32) == r1) big = true;  // runs into the previous tile, or longer than the limit
+                while (b < valid && b - a <= SAB_GSORT_MAX && (u32)(s_key[b + 1] >> 32) == r1) ++b;
+                if (b - a > SAB_GSORT_MAX || (b == valid && (u32)(s_key[valid + 1] >> 32) == r1)) big = true;
+            }
             u32 slot = p;
             if (!big) {
                 u32 before = 0;
