@@ -185,61 +185,6 @@ struct SliceDigit {  // rank whose suffix-array slice [start[g], start[g+1]) hol
     }
 };
 
-// TEXT passes: the keys of the initial sort are never materialised before the first radix pass.  The
-// histogram sweep and the first pass re-derive them from the text: a tile's bytes are staged in shared
-// memory as codes and each thread slides a k-symbol window over ITEMS consecutive positions
-// (key' = (key - lead * top) * radix + next).  The first pass needs no stability (its input order is
-// arbitrary), so the thread-consecutive mapping is free.
-struct TextKeySrc {
-    const u8* text;   // positions >= n_end are past the end of the text (code 0)
-    u64 n_end;
-    const u16* lut;   // byte -> code (1..sigma)
-    u32 radix;        // sigma + 1
-    int k;            // symbols per key
-    u64 top;          // radix^(k-1)
-};
-
-#define SAB_HTEXT_THREADS 512
-#define SAB_HTEXT_ITEMS 8
-#define SAB_HTEXT_TILE (SAB_HTEXT_THREADS * SAB_HTEXT_ITEMS)
-#define SAB_HTEXT_CPAD(o) ((o) + (((o) >> 3) << 1))
-
-__global__ void __launch_bounds__(SAB_HTEXT_THREADS)
-radix_hist_text_kernel(TextKeySrc ts, u64 count, int begin_bit, int npass, u64* __restrict__ ghist) {
-    SAB_SHARED_ARRAY(u32, s_hist, SAB_MAX_PASSES * SAB_RADIX_BINS);
-    // codes padded by one word per 8 elements: thread t starts at word 5t, conflict-free
-    SAB_SHARED_ARRAY(u16, s_code, SAB_HTEXT_CPAD(SAB_HTEXT_TILE + 64) + 8);
-    SAB_SHARED_ARRAY(u16, s_lut, 256);
-    for (int i = threadIdx.x; i < SAB_MAX_PASSES * SAB_RADIX_BINS; i += SAB_HTEXT_THREADS) s_hist[i] = 0;
-    if (threadIdx.x < 256) s_lut[threadIdx.x] = ts.lut[threadIdx.x];
-    __syncthreads();
-    const u64 ntiles = (count + SAB_HTEXT_TILE - 1) / SAB_HTEXT_TILE;
-    for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const u64 base = t * SAB_HTEXT_TILE;
-        for (int o = threadIdx.x; o < SAB_HTEXT_TILE + 64; o += SAB_HTEXT_THREADS) {
-            const u64 i = base + o;
-            s_code[SAB_HTEXT_CPAD(o)] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
-        }
-        __syncthreads();
-        const int o0 = threadIdx.x * SAB_HTEXT_ITEMS;
-        u64 key = 0;
-        for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_HTEXT_CPAD(o0 + q)];
-#pragma unroll
-        for (int j = 0; j < SAB_HTEXT_ITEMS; ++j) {
-            if (base + o0 + j < count) {
-                for (int p = 0; p < npass; ++p)
-                    atomicAdd(&s_hist[p * SAB_RADIX_BINS + ((u32)(key >> (begin_bit + p * SAB_RADIX_BITS)) & 0xffu)], 1u);
-            }
-            key = (key - (u64)s_code[SAB_HTEXT_CPAD(o0 + j)] * ts.top) * ts.radix + (u64)s_code[SAB_HTEXT_CPAD(o0 + j + ts.k)];
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < npass * SAB_RADIX_BINS; i += SAB_HTEXT_THREADS) {
-        const u32 c = s_hist[i];
-        if (c) atomicAdd((unsigned long long*)&ghist[i], (unsigned long long)c);
-    }
-}
-
 // PEER passes (multi-GPU key exchange fused into the partition): bin d is written to the receive
 // buffers of GPU d -- device addresses mapped into this process (symmetric memory), stores travel
 // over NVLink -- at record offset gbase[d] inside them.
@@ -249,11 +194,11 @@ struct PeerOut {
 };
 
 // vals_in may be null when IOTA_VAL (payload = position of the record in the input).
-template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, bool PEER, bool TEXT, int THREADS, int ITEMS>
+template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, bool PEER, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, SAB_ONESWEEP_MIN_BLOCKS)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
                 u32* __restrict__ vals_out, u64 n, DigitOp dop, const u64* __restrict__ gbase,
-                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch, PeerOut po, TextKeySrc ts) {
+                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch, PeerOut po) {
     typedef OnesweepCfg<KeyT, HAS_VAL, IOTA_VAL, THREADS, ITEMS> Cfg;
     static_assert(THREADS >= SAB_RADIX_BINS && THREADS % 32 == 0, "one look-back lane per bin");
     constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE, WTILE = 32 * ITEMS;
@@ -266,12 +211,8 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     SAB_SHARED_ARRAY(u32, s_wsum, 8);
     SAB_SHARED_ARRAY(u64, s_pk, SAB_MAX_RANKS);
     SAB_SHARED_ARRAY(u64, s_pv, SAB_MAX_RANKS);
-    SAB_SHARED_ARRAY(u16, s_lut, 256);
-    static_assert(!TEXT || (sizeof(KeyT) == 8 && IOTA_VAL && (size_t)(THREADS * ITEMS + 64) * 2 * (ITEMS + 2) / ITEMS + 64 <= Cfg::KEY_BYTES),
-                  "TEXT passes build u64 keys with iota payload; the codes are staged in the key area");
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    if (TEXT && tid < 256) s_lut[tid] = ts.lut[tid];
     if (PEER && tid < SAB_MAX_RANKS) {
         s_pk[tid] = po.k[tid];
         s_pv[tid] = po.v[tid];
@@ -292,39 +233,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     const u32 wofs = w * WTILE + lane;
     const KeyT* kin = keys_in + tile_base + wofs;
     const u32* vin = IOTA_VAL ? nullptr : vals_in + tile_base + wofs;
-    if (TEXT) {
-        // keys from the text: lane l of warp w owns ITEMS consecutive positions
-        u16* s_code = (u16*)smem;
-#define SAB_TCPAD(o) ((o) + (((o) / ITEMS) << 1))  // one pad word per lane chunk: lane l starts at word l*(ITEMS/2+1)
-        for (int o = tid; o < TILE + 64; o += THREADS) {
-            const u64 i = tile_base + o;
-            s_code[SAB_TCPAD(o)] = i < ts.n_end ? s_lut[ts.text[i]] : (u16)0;
-        }
-        __syncthreads();
-        if (full) {
-            const u32 o0 = w * WTILE + lane * ITEMS;
-            u64 key = 0;
-            for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_TCPAD(o0 + q)];
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                keys[k] = (KeyT)key;
-                vals[k] = (u32)(tile_base + o0 + k);
-                key = (key - (u64)s_code[SAB_TCPAD(o0 + k)] * ts.top) * ts.radix + (u64)s_code[SAB_TCPAD(o0 + k + ts.k)];
-            }
-        } else {
-            // last tile: warp-striped like every other pass, so the padding records rank behind all real
-            // ones of the last bin (the thread-consecutive mapping would interleave them)
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const u32 o = wofs + k * 32;
-                u64 key = 0;
-                for (int q = 0; q < ts.k; ++q) key = key * ts.radix + (u64)s_code[SAB_TCPAD(o + q)];
-                keys[k] = o < valid ? (KeyT)key : KeyTraits<KeyT>::max_key();
-                vals[k] = (u32)(tile_base + o);
-            }
-        }
-        // the staged codes are overwritten by the scatter, two barriers further down
-    } else if (full) {
+    if (full) {
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) keys[k] = kin[k * 32];
         if (HAS_VAL) {

@@ -27,9 +27,6 @@
 #include "sab_group_sort.cuh"
 
 #define SAB_RANK_EMPTY 0xffffffffu
-#ifndef SAB_TEXT_KEYS
-#define SAB_TEXT_KEYS 0
-#endif
 #define SAB_PAD(o) ((o) + ((o) >> 5))  // shared-memory padding, one word per 32; NB: evaluates its argument twice
 // 1: the records of a round are ordered inside their groups by sab_group_sort (one sweep + a radix sort
 // of the large groups only) instead of a radix sort of every record
@@ -366,30 +363,6 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
 
     const u64 top = sab_pow_u64(base, k - 1);
-#if SAB_TEXT_KEYS
-    sab_prof_end(c);
-    // 2 + 3 (variant, off by default: measured 3 ms slower per GiB than packing first, profiles/r01_variants.md):
-    // the keys are derived from the text inside the histogram sweep and the first radix pass
-    TextKeySrc ts;
-    ts.text = d_text;
-    ts.n_end = n;
-    ts.lut = d_lut;
-    ts.radix = base;
-    ts.k = k;
-    ts.top = top;
-    bool materialised = false;
-    SAB_TRY(sab_radix_sort_text(c, buf, n, key_bits, ts, &S.passes[0], &materialised));
-    if (!materialised) {  // degenerate: every key shares every digit (e.g. n == 1); pack explicitly
-        sab_prof_begin(c, 2);
-        SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
-                   (const u16*)d_lut, base, k, top, buf.k[buf.cur]);
-        SAB_LAUNCH_CHECK();
-        SAB_LAUNCH(iota_kernel, (unsigned)div_up64(n, 256), 256, 0, st, buf.v[buf.cur], n);
-        sab_prof_end(c);
-        SAB_LAUNCH_CHECK();
-        S.kernel_launches += 2;
-    }
-#else
     // 2. packed keys
     SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
                (const u16*)d_lut, base, k, top, buf.k[0]);
@@ -399,7 +372,6 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
 
     // 3. sort (key, i); the payload of the first pass is generated, not read
     SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, key_bits, /*iota=*/true, &S.passes[0]));
-#endif
 
     // 4. ranks, SA skeleton, active list, bucket directory over the sorted keys
     u32* d_m = c->d_counters;

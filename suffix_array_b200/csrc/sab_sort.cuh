@@ -28,9 +28,9 @@ struct PassShape<u32> {
     static constexpr int THREADS = SAB_PASS_THREADS, ITEMS = SAB_PASS_ITEMS;
 };
 
-template <typename KeyT, bool IOTA, typename DigitOp, bool PEER = false, bool TEXT = false>
+template <typename KeyT, bool IOTA, typename DigitOp, bool PEER = false>
 static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, DigitOp dop,
-                              const u64* gbase, const PeerOut* peer = nullptr, const TextKeySrc* text = nullptr) {
+                              const u64* gbase, const PeerOut* peer = nullptr) {
     constexpr int THREADS = PassShape<KeyT>::THREADS, ITEMS = PassShape<KeyT>::ITEMS;
     typedef OnesweepCfg<KeyT, true, IOTA, THREADS, ITEMS> Cfg;
     const u64 tiles = div_up64(n, (u64)Cfg::TILE);
@@ -39,19 +39,16 @@ static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const 
         c->lb_epoch = 0;
     }
     const u32 epoch = ++c->lb_epoch;
-    auto kern = onesweep_kernel<KeyT, DigitOp, true, IOTA, PEER, TEXT, THREADS, ITEMS>;
+    auto kern = onesweep_kernel<KeyT, DigitOp, true, IOTA, PEER, THREADS, ITEMS>;
     PeerOut po;
     memset(&po, 0, sizeof(po));
     if (PEER && peer) po = *peer;
-    TextKeySrc ts;
-    memset(&ts, 0, sizeof(ts));
-    if (TEXT && text) ts = *text;
 #ifndef SAB_EMU
     SAB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));  // per device
 #endif
     sab_prof_begin(c, 0);
     SAB_LAUNCH(kern, (unsigned)tiles, THREADS, Cfg::SMEM, c->stream, kin, kout, vin, vout, n, dop, gbase,
-               c->d_lookback, c->d_ticket, c->ticket_host, epoch, po, ts);
+               c->d_lookback, c->d_ticket, c->ticket_host, epoch, po);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     c->ticket_host += (u32)tiles;
@@ -126,57 +123,6 @@ static int sab_radix_sort(SabContext* c, SortBuffers<KeyT>& buf, u64 n, int begi
         SAB_LAUNCH(iota_kernel, (unsigned)div_up64(n, 256), 256, 0, c->stream, buf.v[buf.cur], n);
         SAB_LAUNCH_CHECK();
         c->stats.kernel_launches += 1;
-    }
-    return SAB_OK;
-}
-
-// Initial sort of the suffixes by their packed keys WITHOUT a materialised key array: the histogram
-// sweep and the first executed pass derive the keys from the text (TextKeySrc), later passes run on
-// the (key, index) records the first one wrote.  buf.k[*] / buf.v[*] are scratch; on return buf.cur
-// names the sorted records.  *materialised = false when no pass ran at all (every key has the same
-// digits everywhere): the caller must then pack the keys itself.
-static int sab_radix_sort_text(SabContext* c, SortBuffers<u64>& buf, u64 n, int key_bits, const TextKeySrc& ts,
-                               u32* passes_out, bool* materialised) {
-    *passes_out = 0;
-    *materialised = false;
-    if (n == 0) return SAB_OK;
-    const int npass = (key_bits + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
-    if (npass < 1 || npass > SAB_MAX_PASSES) {
-        sab_set_error("radix sort: bad key width %d", key_bits);
-        return SAB_ERR_INTERNAL;
-    }
-    constexpr int TILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
-    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(n, TILE)));
-    SAB_CUDA_TRY(cudaMemsetAsync(c->d_ghist, 0, sizeof(u64) * SAB_MAX_PASSES * SAB_RADIX_BINS, c->stream));
-    u64 hblocks = div_up64(n, (u64)SAB_HTEXT_TILE);
-    const u64 hmax = (u64)c->sm_count * 3;
-    if (hblocks > hmax) hblocks = hmax;
-    sab_prof_begin(c, 1);
-    SAB_LAUNCH(radix_hist_text_kernel, (unsigned)hblocks, SAB_HTEXT_THREADS, 0, c->stream, ts, n, 0, npass, c->d_ghist);
-    SAB_LAUNCH_CHECK();
-    SAB_LAUNCH(radix_scan_kernel, 1, SAB_RADIX_BINS, 0, c->stream, (const u64*)c->d_ghist, n, npass, c->d_gbase, c->d_skip);
-    sab_prof_end(c);
-    SAB_LAUNCH_CHECK();
-    c->stats.kernel_launches += 2;
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, c->d_skip, sizeof(u32) * SAB_MAX_PASSES, cudaMemcpyDeviceToHost, c->stream));
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    u32 skip[SAB_MAX_PASSES];
-    memcpy(skip, c->h_small, sizeof(skip));
-    for (int p = 0; p < npass; ++p) {
-        if (skip[p]) continue;
-        const int in = buf.cur, out = buf.cur ^ 1;
-        ShiftDigit<u64> dop;
-        dop.shift = p * SAB_RADIX_BITS;
-        if (!*materialised) {
-            SAB_TRY((sab_launch_pass_op<u64, true, ShiftDigit<u64>, false, true>(c, (const u64*)nullptr, buf.k[out], nullptr, buf.v[out],
-                                                                                n, dop, c->d_gbase + p * SAB_RADIX_BINS, nullptr, &ts)));
-            *materialised = true;
-        } else {
-            SAB_TRY((sab_launch_pass_op<u64, false, ShiftDigit<u64> >(c, buf.k[in], buf.k[out], buf.v[in], buf.v[out], n, dop,
-                                                                      c->d_gbase + p * SAB_RADIX_BINS)));
-        }
-        buf.cur = out;
-        *passes_out += 1;
     }
     return SAB_OK;
 }
