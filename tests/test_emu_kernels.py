@@ -63,3 +63,23 @@ def test_emu_pack(emu_backend, oracle):
 def SuffixArrayBanana():
     from suffix_array_b200 import SuffixArray
     return SuffixArray(b"banana").dump_bytes()
+
+
+def test_emu_group_sort_boundaries(emu_backend, oracle):
+    """Rounds whose groups sit right at the limits of group_sort_kernel: a random block repeated r times gives
+    groups of r records (r = 32: ordered in shared memory, r = 33: radix path), lists longer than one
+    2048-record tile (groups cut by tile borders), and mixtures of both kinds."""
+    from suffix_array_b200 import _lib
+    rng = np.random.default_rng(77)
+    for r, blk in ((31, 97), (32, 90), (33, 90), (34, 61), (2, 1500), (3, 1100)):
+        block = rng.integers(0, 4, blk, dtype=np.uint8)
+        t = np.concatenate([np.tile(block, r), rng.integers(0, 4, 50, dtype=np.uint8)])
+        pc.check_construction(oracle, t)
+        st = _lib.last_stats()
+        assert st["group_sort_records"] > 0, (r, blk, st)
+    # small and large groups interleaved in one list
+    a = np.tile(rng.integers(0, 4, 70, dtype=np.uint8), 40)
+    b = np.tile(rng.integers(0, 4, 400, dtype=np.uint8), 3)
+    pc.check_construction(oracle, np.concatenate([a, rng.integers(0, 4, 3000, dtype=np.uint8), b]))
+    st = _lib.last_stats()
+    assert st["group_sort_records"] > st["group_big_records"] > 0, st
