@@ -54,12 +54,19 @@ int32_t sab200_dist_init_ranks(const uint64_t* d_keys, const uint32_t* d_idx, ui
                                uint32_t* d_sa_local, uint32_t* d_rank_seq, uint32_t* d_act_r1, uint32_t* d_act_idx,
                                uint64_t* n_active, int32_t device);
 
-/* Stable partition of (key, val) u32 pairs by the owner rank of text position key + add under block
- * width B (owner = min((key + add) / B, P-1)); keys equal to 0xFFFFFFFF are dropped (they sort behind
- * the last rank and are not counted).  counts (host, P x u64). */
+/* Layout of the distributed rank[] array, named by (B, P, cyc_shift) in the calls below:
+ *   cyc_shift < 0  block layout: GPU g owns positions [g*B, (g+1)*B), the last GPU also the tail (position n);
+ *                  local slot of position q = q - g*B
+ *   cyc_shift >= 0 block-cyclic layout, B = 2^cyc_shift: owner = (q >> cyc_shift) mod P,
+ *                  local slot = ((q >> cyc_shift) / P) << cyc_shift | (q mod B).  Every region of the text is
+ *                  spread over all GPUs, so the rank requests of a round do not pile up on the owners of the
+ *                  region they point into (measured on the mixed 3.9 GiB text, profiles/r01_multi_gpu.md).
+ *
+ * Stable partition of (key, val) u32 pairs by the owner of text position key + add; keys equal to 0xFFFFFFFF
+ * are dropped (they sort behind the last rank and are not counted).  counts (host, P x u64). */
 int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint32_t* d_val, uint64_t count, uint32_t add,
-                                    uint32_t B, int32_t P, uint32_t* d_key_out, uint32_t* d_val_out, uint64_t* counts,
-                                    int32_t device);
+                                    uint32_t B, int32_t P, int32_t cyc_shift, uint32_t* d_key_out, uint32_t* d_val_out,
+                                    uint64_t* counts, int32_t device);
 
 /* Stable partition of (pos, val) u32 pairs by the rank whose suffix-array slice holds SA position pos:
  * slice_start (host, P x u32) = first SA position of every rank's slice, ascending; pos equal to
@@ -69,13 +76,13 @@ int32_t sab200_dist_partition_slices(const uint32_t* d_pos, const uint32_t* d_va
                                      const uint32_t* slice_start, int32_t P, uint32_t* d_pos_out, uint32_t* d_val_out,
                                      uint64_t* counts, int32_t device);
 
-/* d_rank_local[d_pos[t] - lo] = d_val[t]   (ranks arriving at their owner; also SA entries arriving at
- * the owner of their slice, with lo = the slice offset) */
-int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo,
-                            uint32_t* d_rank_local, int32_t device);
-/* d_out[t] = d_rank_local[d_pos[t] + add - lo]   (answering rank[i+h] requests) */
-int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo,
-                           const uint32_t* d_rank_local, uint32_t* d_out, int32_t device);
+/* d_rank_local[slot(d_pos[t])] = d_val[t]: ranks arriving at their owner (slot = d_pos[t] - lo under the
+ * block layout); also SA entries arriving at the owner of their slice (block layout, lo = slice offset). */
+int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo, uint32_t B,
+                            int32_t P, int32_t cyc_shift, uint32_t* d_rank_local, int32_t device);
+/* d_out[t] = d_rank_local[slot(d_pos[t] + add)]   (answering rank[i+h] requests) */
+int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo, uint32_t B, int32_t P,
+                           int32_t cyc_shift, const uint32_t* d_rank_local, uint32_t* d_out, int32_t device);
 /* d_key64[t] = (d_r1[t] << 32) | d_r2[t] */
 int32_t sab200_dist_make_keys(const uint32_t* d_r1, const uint32_t* d_r2, uint64_t count, uint64_t* d_key64,
                               int32_t device);
@@ -91,15 +98,14 @@ int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint6
                            uint32_t* d_upd_r, uint32_t* d_set_pos, uint64_t* n_kept, int32_t device);
 
 /* Peer-to-peer form of the round exchanges (NVLink): peer_rank_ptrs (host array of P device addresses)
- * are the rank[] blocks of all GPUs mapped into this process (symmetric memory; block g holds the ranks
- * of text positions [g*B, (g+1)*B), the last block also position n).
+ * are the rank[] arrays of all GPUs mapped into this process (symmetric memory; layout as above).
  *   gather:  d_key64[t] = (d_r1[t] << 32) | rank[d_idx[t] + h], loaded from the owner GPU
  *   scatter: rank[d_idx[t]] = d_val[t] stored into the owner GPU (d_idx[t] == 0xFFFFFFFF: skip)
  * The caller orders the phases across ranks (nobody writes while anyone still reads). */
 int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint64_t m, uint32_t h, uint32_t B, int32_t P,
-                               const uint64_t* peer_rank_ptrs, uint64_t* d_key64, int32_t device);
+                               int32_t cyc_shift, const uint64_t* peer_rank_ptrs, uint64_t* d_key64, int32_t device);
 int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
-                                const uint64_t* peer_rank_ptrs, int32_t device);
+                                int32_t cyc_shift, const uint64_t* peer_rank_ptrs, int32_t device);
 
 /* Key exchange fused into the partition kernel.  count_keys: counts (host, P x u64) per destination.
  * partition_keys_p2p: the partition pass stores destination d's records straight into GPU d's receive

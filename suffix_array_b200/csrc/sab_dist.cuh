@@ -22,14 +22,19 @@ __global__ void iota_base_kernel(u32* __restrict__ out, u64 n, u32 base) {
     if (i < n) out[i] = base + (u32)i;
 }
 __global__ void hist_widen_kernel(const u32* __restrict__ h32, u64* __restrict__ h64) { h64[threadIdx.x] = h32[threadIdx.x]; }
-__global__ void dist_scatter_kernel(const u32* __restrict__ pos, const u32* __restrict__ val, u64 n, u32 lo, u32* __restrict__ rank_local) {
+// local slot of position q on its owner: q - lo under the block layout (lay.cyc = 0), lay.slot() otherwise
+__global__ void dist_scatter_kernel(const u32* __restrict__ pos, const u32* __restrict__ val, u64 n, u32 lo, RankLayout lay,
+                                    u32* __restrict__ rank_local) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rank_local[pos[i] - lo] = val[i];
+    if (i < n) rank_local[lay.cyc ? lay.slot(pos[i], 0) : (u64)(pos[i] - lo)] = val[i];
 }
-__global__ void dist_gather_kernel(const u32* __restrict__ pos, u64 n, u32 add, u32 lo, const u32* __restrict__ rank_local,
-                                   u32* __restrict__ out) {
+__global__ void dist_gather_kernel(const u32* __restrict__ pos, u64 n, u32 add, u32 lo, RankLayout lay,
+                                   const u32* __restrict__ rank_local, u32* __restrict__ out) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = rank_local[(u64)pos[i] + add - lo];
+    if (i < n) {
+        const u64 q = (u64)pos[i] + add;
+        out[i] = rank_local[lay.cyc ? lay.slot(q, 0) : q - lo];
+    }
 }
 __global__ void dist_make_keys_kernel(const u32* __restrict__ r1, const u32* __restrict__ r2, u64 n, u64* __restrict__ key64) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,16 +189,14 @@ extern "C" int32_t sab200_dist_init_ranks(const uint64_t* d_keys, const uint32_t
 }
 
 extern "C" int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint32_t* d_val, uint64_t count, uint32_t add,
-                                               uint32_t B, int32_t P, uint32_t* d_key_out, uint32_t* d_val_out,
-                                               uint64_t* counts, int32_t device) {
+                                               uint32_t B, int32_t P, int32_t cyc_shift, uint32_t* d_key_out,
+                                               uint32_t* d_val_out, uint64_t* counts, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
-    if (P < 1 || P > SAB_MAX_RANKS || B == 0 || !counts) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
     OwnerDigit dop;
     dop.add = add;
-    dop.B = B;
-    dop.pmax = (u32)P - 1;
+    if (P > SAB_MAX_RANKS || !counts || sab_rank_layout(B, P, cyc_shift, &dop.lay) != 0) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
     SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, d_key, count, dop, P, counts)));
     if (count) {
         constexpr int TILE = PassShape<u32>::THREADS * PassShape<u32>::ITEMS;
@@ -224,26 +227,31 @@ extern "C" int32_t sab200_dist_partition_slices(const uint32_t* d_pos, const uin
     return SAB_OK;
 }
 
-extern "C" int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo,
-                                       uint32_t* d_rank_local, int32_t device) {
+extern "C" int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo, uint32_t B,
+                                       int32_t P, int32_t cyc_shift, uint32_t* d_rank_local, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
+    RankLayout lay;
+    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
     std::lock_guard<std::mutex> lk(c->mu);
     if (count) {
-        SAB_LAUNCH(dist_scatter_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, d_val, count, lo, d_rank_local);
+        SAB_LAUNCH(dist_scatter_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, d_val, count, lo, lay, d_rank_local);
         SAB_LAUNCH_CHECK();
     }
     SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SAB_OK;
 }
 
-extern "C" int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo,
-                                      const uint32_t* d_rank_local, uint32_t* d_out, int32_t device) {
+extern "C" int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo, uint32_t B, int32_t P,
+                                      int32_t cyc_shift, const uint32_t* d_rank_local, uint32_t* d_out, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
+    RankLayout lay;
+    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
     std::lock_guard<std::mutex> lk(c->mu);
     if (count) {
-        SAB_LAUNCH(dist_gather_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, count, add, lo, d_rank_local, d_out);
+        SAB_LAUNCH(dist_gather_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, count, add, lo, lay, d_rank_local,
+                   d_out);
         SAB_LAUNCH_CHECK();
     }
     SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -316,29 +324,27 @@ struct PeerTable {
     u32* p[SAB_MAX_RANKS];
 };
 
-// key64[t] = (r1[t] << 32) | rank[idx[t] + h], rank[] block-distributed with width B over pmax+1 GPUs
+// key64[t] = (r1[t] << 32) | rank[idx[t] + h], rank[] distributed over the GPUs as `lay` says
 __global__ void __launch_bounds__(256)
-dist_gather_p2p_kernel(const u32* __restrict__ r1, const u32* __restrict__ idx, u64 m, u32 h, u32 B, u32 pmax, PeerTable pt,
+dist_gather_p2p_kernel(const u32* __restrict__ r1, const u32* __restrict__ idx, u64 m, u32 h, RankLayout lay, PeerTable pt,
                        u64* __restrict__ key64) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
     const u64 q = (u64)idx[t] + h;
-    u32 o = (u32)(q / B);
-    if (o > pmax) o = pmax;
-    const u32 r2 = pt.p[o][q - (u64)o * B];
+    const u32 o = lay.owner(q);
+    const u32 r2 = pt.p[o][lay.slot(q, o)];
     key64[t] = ((u64)r1[t] << 32) | r2;
 }
 
 // rank[idx[t]] = val[t] on the owner of idx[t]; idx == 0xFFFFFFFF marks "nothing to write"
 __global__ void __launch_bounds__(256)
-dist_scatter_p2p_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 count, u32 B, u32 pmax, PeerTable pt) {
+dist_scatter_p2p_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 count, RankLayout lay, PeerTable pt) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const u32 i = idx[t];
     if (i == 0xffffffffu) return;
-    u32 o = i / B;
-    if (o > pmax) o = pmax;
-    pt.p[o][i - o * B] = val[t];
+    const u32 o = lay.owner(i);
+    pt.p[o][lay.slot(i, o)] = val[t];
 }
 
 static int sab_peer_table(const uint64_t* peer_ptrs, int32_t P, PeerTable* pt) {
@@ -348,16 +354,18 @@ static int sab_peer_table(const uint64_t* peer_ptrs, int32_t P, PeerTable* pt) {
 }
 
 extern "C" int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint64_t m, uint32_t h, uint32_t B,
-                                          int32_t P, const uint64_t* peer_rank_ptrs, uint64_t* d_key64, int32_t device) {
+                                          int32_t P, int32_t cyc_shift, const uint64_t* peer_rank_ptrs, uint64_t* d_key64,
+                                          int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
     PeerTable pt;
     SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
-    if (B == 0) return SAB_ERR_ARGS;
+    RankLayout lay;
+    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
     std::lock_guard<std::mutex> lk(c->mu);
     if (m) {
         sab_prof_begin(c, 4);
-        SAB_LAUNCH(dist_gather_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, c->stream, d_r1, d_idx, m, h, B, (u32)P - 1, pt, d_key64);
+        SAB_LAUNCH(dist_gather_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, c->stream, d_r1, d_idx, m, h, lay, pt, d_key64);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         c->stats.kernel_launches++;
@@ -367,16 +375,17 @@ extern "C" int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* 
 }
 
 extern "C" int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
-                                           const uint64_t* peer_rank_ptrs, int32_t device) {
+                                           int32_t cyc_shift, const uint64_t* peer_rank_ptrs, int32_t device) {
     SabContext* c = sab_dist_ctx(device);
     if (!c) return SAB_ERR_CUDA;
     PeerTable pt;
     SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
-    if (B == 0) return SAB_ERR_ARGS;
+    RankLayout lay;
+    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
     std::lock_guard<std::mutex> lk(c->mu);
     if (count) {
         sab_prof_begin(c, 3);
-        SAB_LAUNCH(dist_scatter_p2p_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_idx, d_val, count, B, (u32)P - 1, pt);
+        SAB_LAUNCH(dist_scatter_p2p_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_idx, d_val, count, lay, pt);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         c->stats.kernel_launches++;

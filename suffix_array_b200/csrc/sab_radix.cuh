@@ -164,12 +164,38 @@ struct SplitterDigit {  // destination rank of a key: number of splitters <= key
         return d;
     }
 };
-struct OwnerDigit {  // owner rank of text position key + add under a block distribution of width B
-    u32 add, B, pmax;
-    __device__ __forceinline__ u32 operator()(u32 k) const {
-        if (k == 0xffffffffu) return pmax + 1u;  // dropped record / tile padding: behind the last rank
-        const u32 o = (u32)(((u64)k + add) / B);
+// Which GPU owns rank[q] (multi-GPU), and at which slot of its local array.
+//   block  (cyc = 0): GPU g owns positions [g*B, (g+1)*B), the last GPU also the tail; slot = q - g*B
+//   cyclic (cyc = 1): blocks of B = 2^shift positions are dealt round-robin: owner = (q >> shift) mod P,
+//                     slot = ((q >> shift) / P) << shift | (q mod B) -- any region of the text is spread over
+//                     all GPUs, so the requests of a round do not pile up on the owners of one region
+struct RankLayout {
+    u32 B, pmax, cyc, shift;
+    __device__ __forceinline__ u32 owner(u64 q) const {
+        if (cyc) return (u32)((q >> shift) % (pmax + 1u));
+        const u32 o = (u32)(q / B);
         return o < pmax ? o : pmax;
+    }
+    __device__ __forceinline__ u64 slot(u64 q, u32 o) const {
+        if (cyc) return (((q >> shift) / (pmax + 1u)) << shift) | (q & (u64)(B - 1u));
+        return q - (u64)o * B;
+    }
+};
+static inline int sab_rank_layout(u32 B, int P, int cyc_shift, RankLayout* L) {
+    if (P < 1 || P > 16 || B == 0) return -1;
+    L->B = B;
+    L->pmax = (u32)P - 1u;
+    L->cyc = cyc_shift >= 0 ? 1u : 0u;
+    L->shift = cyc_shift >= 0 ? (u32)cyc_shift : 0u;
+    if (L->cyc && (cyc_shift > 31 || B != (1u << cyc_shift))) return -1;
+    return 0;
+}
+struct OwnerDigit {  // owner rank of text position key + add
+    u32 add;
+    RankLayout lay;
+    __device__ __forceinline__ u32 operator()(u32 k) const {
+        if (k == 0xffffffffu) return lay.pmax + 1u;  // dropped record / tile padding: behind the last rank
+        return lay.owner((u64)k + add);
     }
 };
 

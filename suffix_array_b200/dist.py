@@ -35,6 +35,31 @@ P2P_MAX_RECORDS = int(os.environ.get("SAB_P2P_MAX_RECORDS", 16 << 20))
 # Active lists are evened out across the ranks (see _rebalance) when they average at least this many records
 # per rank and the longest exceeds the mean by 10 %: below that a round is launch-bound anyway.
 REBALANCE_MIN_RECORDS = int(os.environ.get("SAB_REBALANCE_MIN", 1 << 20))
+# "block": GPU g owns the ranks of its own text shard; "cyclic": blocks of up to 1 Mi positions dealt
+# round-robin (RankLayout).  Cyclic balances the owner-side work of the rounds on texts whose regions differ
+# (profiles/r01_multi_gpu.md); it is exercised by the gloo tests and becomes the default once its
+# peer-to-peer kernels have been validated on GPUs.
+RANK_LAYOUT = os.environ.get("SAB_RANK_LAYOUT", "block")
+
+
+class RankLayout:
+    """Distribution of rank[] over the GPUs (see include/sab200_dist.h): block (GPU g owns the ranks of its
+    own text shard) or block-cyclic (blocks of 2^shift positions dealt round-robin).  `width`, `shift` are
+    the (B, cyc_shift) arguments of the C steps; `local_len` = entries of every GPU's local array."""
+
+    def __init__(self, n, P, kind):
+        B = max(1, -(-n // P))
+        if kind == "cyclic":
+            # about 8 blocks per GPU at least, at most 1 Mi positions per block
+            self.shift = max(0, min(20, (max(1, n // (8 * P))).bit_length() - 1))
+            self.width = 1 << self.shift
+            blocks = -(-(n + 1) // self.width)          # positions 0 .. n
+            self.local_len = (-(-blocks // P)) << self.shift
+        else:
+            self.shift = -1
+            self.width = B
+            self.local_len = B + 1                      # the last GPU also owns position n
+        self.kind = kind
 
 
 def shard_bounds(n, rank, world):
@@ -59,18 +84,18 @@ def _bind(L):
         "sab200_dist_partition_keys": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
         "sab200_dist_sort_pairs": [vp, vp, vp, vp, u64, i32, i32],
         "sab200_dist_init_ranks": [vp, vp, u64, u32, vp, vp, vp, vp, C.POINTER(u64), i32],
-        "sab200_dist_partition_owner": [vp, vp, u64, u32, u32, i32, vp, vp, vp, i32],
-        "sab200_dist_scatter": [vp, vp, u64, u32, vp, i32],
-        "sab200_dist_gather": [vp, u64, u32, u32, vp, vp, i32],
+        "sab200_dist_partition_owner": [vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, i32],
+        "sab200_dist_scatter": [vp, vp, u64, u32, u32, i32, i32, vp, i32],
+        "sab200_dist_gather": [vp, u64, u32, u32, u32, i32, i32, vp, vp, i32],
         "sab200_dist_make_keys": [vp, vp, u64, vp, i32],
         "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
         "sab200_dist_partition_slices": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
         "sab200_dist_begin": [i32],
         "sab200_dist_end": [i32],
-        "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, vp, vp, i32],
+        "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, i32, vp, vp, i32],
         "sab200_dist_count_keys": [vp, u64, vp, i32, vp, i32],
         "sab200_dist_partition_keys_p2p": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
-        "sab200_dist_scatter_p2p": [vp, vp, u64, u32, i32, vp, i32],
+        "sab200_dist_scatter_p2p": [vp, vp, u64, u32, i32, i32, vp, i32],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -168,16 +193,16 @@ def _peer_recv(cx, cap):
     return _PEER_CACHE[key][:4]
 
 
-def _peer_ranks(cx, B):
-    """The rank[] block of every GPU (B + 1 u32 each), mapped into this process through torch's
-    symmetric memory: returns (local block tensor, uint64 array of the P peer addresses).
-    Cached per (device, P, B): the rendezvous is a collective and not cheap."""
-    key = ("rank", str(cx.device), cx.P, B, id(cx.group))
+def _peer_ranks(cx, length):
+    """The rank[] array of every GPU (`length` u32 each), mapped into this process through torch's
+    symmetric memory: returns (local array tensor, uint64 array of the P peer addresses).
+    Cached per (device, P, length): the rendezvous is a collective and not cheap."""
+    key = ("rank", str(cx.device), cx.P, length, id(cx.group))
     if key not in _PEER_CACHE:
         for old in [k_ for k_ in _PEER_CACHE if k_[0] == "rank"]:
             del _PEER_CACHE[old]
         import torch.distributed._symmetric_memory as symm
-        t = symm.empty(B + 1, dtype=torch.int32, device=cx.device)
+        t = symm.empty(length, dtype=torch.int32, device=cx.device)
         hdl = symm.rendezvous(t, cx.group if cx.group is not None else dist.group.WORLD)
         ptrs = np.array([int(p) for p in hdl.buffer_ptrs], dtype=np.uint64)
         _PEER_CACHE[key] = (t, ptrs, hdl)
@@ -191,24 +216,24 @@ def _barrier(cx):
     cx.collectives += 1
 
 
-def _to_owner(cx, keys, vals, count, add, B):
+def _to_owner(cx, keys, vals, count, add, lay):
     """Stable partition of (keys, vals) by the owner of position keys+add; returns the partitioned
     buffers and the per-destination counts (records whose key is 0xFFFFFFFF are dropped)."""
     kp = cx.empty(count, torch.int32)
     vp = cx.empty(count, torch.int32)
     cnt = np.zeros(cx.P, dtype=np.uint64)
-    cx.call("sab200_dist_partition_owner", _p(keys), _p(vals), count, add, B, cx.P, _p(kp), _p(vp),
+    cx.call("sab200_dist_partition_owner", _p(keys), _p(vals), count, add, lay.width, cx.P, lay.shift, _p(kp), _p(vp),
                                               cnt.ctypes.data_as(C.c_void_p), cx.dev)
     return kp, vp, [int(x) for x in cnt]
 
 
-def _send_ranks(cx, idx, ranks, count, B, lo, rank_local):
+def _send_ranks(cx, idx, ranks, count, lay, lo, rank_local):
     """rank[idx[t]] = ranks[t] on the GPU that owns text position idx[t]."""
-    kp, vp, send = _to_owner(cx, idx, ranks, count, 0, B)
+    kp, vp, send = _to_owner(cx, idx, ranks, count, 0, lay)
     recv = cx.exchange_counts(send)
     ri = cx.all_to_all(kp, send, recv)
     rr = cx.all_to_all(vp, send, recv)
-    cx.call("sab200_dist_scatter", _p(ri), _p(rr), ri.numel(), lo, _p(rank_local), cx.dev)
+    cx.call("sab200_dist_scatter", _p(ri), _p(rr), ri.numel(), lo, lay.width, cx.P, lay.shift, _p(rank_local), cx.dev)
 
 
 def _next_group_boundary(r1, c, m):
@@ -269,7 +294,7 @@ def _send_sa(cx, pos, idx, count, starts, sa_off, sa_local):
     recv = cx.exchange_counts(send)
     rp = cx.all_to_all(kp, send, recv)
     ri = cx.all_to_all(vp, send, recv)
-    cx.call("sab200_dist_scatter", _p(rp), _p(ri), rp.numel(), sa_off, _p(sa_local), cx.dev)
+    cx.call("sab200_dist_scatter", _p(rp), _p(ri), rp.numel(), sa_off, 1, cx.P, -1, _p(sa_local), cx.dev)  # slices are contiguous
 
 
 def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
@@ -293,10 +318,11 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         raise ValueError("text longer than MAX_LENGTH")
     B, lo, hi = shard_bounds(n, rank, P)
     count = hi - lo
+    lay = RankLayout(n, P, RANK_LAYOUT)
     use_p2p = False
     if exchange in ("auto", "p2p") and cx.device.type == "cuda" and n > 0:
         try:
-            rank_local, peer_ptrs = _peer_ranks(cx, B)
+            rank_local, peer_ptrs = _peer_ranks(cx, lay.local_len)
             use_p2p = True
         except Exception as e:  # noqa: BLE001 -- any failure to map peers falls back to the collective path
             if exchange == "p2p":
@@ -411,12 +437,12 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         rank_local.zero_()  # slot of position n (the empty suffix) must read 0
         _barrier(cx)        # nobody stores into a block that is still being cleared
         if B <= P2P_MAX_RECORDS:
-            cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, B, P, peer_arg, cx.dev)
+            cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, lay.width, P, lay.shift, peer_arg, cx.dev)
         else:
-            _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
+            _send_ranks(cx, vs, rank_seq, R, lay, lo, rank_local)
     else:
-        rank_local = torch.zeros(count + 1, dtype=torch.int32, device=cx.device)  # slot `count` = position n if owned
-        _send_ranks(cx, vs, rank_seq, R, B, lo, rank_local)
+        rank_local = torch.zeros(lay.local_len, dtype=torch.int32, device=cx.device)  # the slot of position n reads 0
+        _send_ranks(cx, vs, rank_seq, R, lay, lo, rank_local)
     del ks, vs, k0, k1, v0, v1, rank_seq
     cx.mark("ranks_to_owners")
     # 6. doubling rounds
@@ -443,17 +469,17 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         p2p_round = use_p2p and tot <= P2P_MAX_RECORDS * P  # same decision on every rank
         if p2p_round:
             # the all_reduce above ordered every rank's previous stores before these loads
-            cx.call("sab200_dist_gather_p2p", _p(cur_r1), _p(cur_idx), m, h, B, P, peer_arg, _p(key64), cx.dev)
+            cx.call("sab200_dist_gather_p2p", _p(cur_r1), _p(cur_idx), m, h, lay.width, P, lay.shift, peer_arg, _p(key64), cx.dev)
             ipart = cur_idx
         else:
             # requests i+h to the owners, answers back in the same order
-            ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, B)
+            ipart, rpart, send = _to_owner(cx, cur_idx, cur_r1, m, h, lay)
             cx.trace("rounds/partition_requests")
             recv = cx.exchange_counts(send)
             q = cx.all_to_all(ipart, send, recv)
             cx.trace("rounds/send_requests")
             ans = cx.empty(q.numel(), torch.int32)
-            cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, _p(rank_local), _p(ans), cx.dev)
+            cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, lay.width, P, lay.shift, _p(rank_local), _p(ans), cx.dev)
             cx.trace("rounds/gather")
             r2 = cx.all_to_all(ans, recv, send)
             cx.trace("rounds/send_answers")
@@ -483,9 +509,9 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         del set_pos, si, ipart, idx_tmp, cur_r1, cur_idx
         if p2p_round:
             _barrier(cx)  # every rank has finished loading ranks of this round
-            cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, B, P, peer_arg, cx.dev)
+            cx.call("sab200_dist_scatter_p2p", _p(upd_idx), _p(upd_r), m, lay.width, P, lay.shift, peer_arg, cx.dev)
         else:
-            _send_ranks(cx, upd_idx, upd_r, m, B, lo, rank_local)
+            _send_ranks(cx, upd_idx, upd_r, m, lay, lo, rank_local)
         del upd_idx, upd_r
         cx.trace("rounds/update_ranks")
         m = kept.value
@@ -496,7 +522,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
     if stats is not None:
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
-                      "exchange": "p2p" if use_p2p else "collective", "rebalanced": rebalanced,
+                      "exchange": "p2p" if use_p2p else "collective", "rebalanced": rebalanced, "rank_layout": lay.kind,
                       "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()},
                       "wall_ms": round((time.perf_counter() - t_enter) * 1e3, 2)})
     return sa_local, sa_off

@@ -83,3 +83,53 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
     pc.check_construction(oracle, np.concatenate([a, rng.integers(0, 4, 3000, dtype=np.uint8), b]))
     st = _lib.last_stats()
     assert st["group_sort_records"] > st["group_big_records"] > 0, st
+
+
+def test_emu_peer_rank_kernels_both_layouts(emu_lib):
+    """The peer-to-peer gather / scatter kernels of the multi-GPU rounds against a numpy model of both rank[]
+    layouts: the "peers" are P separate arrays of this process (the emulator's device memory is host memory)."""
+    import ctypes as C
+    from suffix_array_b200 import dist as sdist
+    L = sdist._bind(emu_lib)
+    rng = np.random.default_rng(5)
+    for n, P in ((1000, 3), (4097, 2), (70000, 8), (5, 4)):
+        for kind in ("block", "cyclic"):
+            lay = sdist.RankLayout(n, P, kind)
+
+            def owner_slot(q):
+                if kind == "cyclic":
+                    b = q >> lay.shift
+                    return b % P, ((b // P) << lay.shift) | (q & (lay.width - 1))
+                o = min(q // lay.width, P - 1)
+                return o, q - o * lay.width
+
+            peers = [np.full(lay.local_len, 0xDEADBEEF, dtype=np.uint32) for _ in range(P)]
+            ptrs = np.array([p.ctypes.data for p in peers], dtype=np.uint64)
+            # every position 0..n lands in exactly one slot, inside the local arrays
+            seen = set()
+            for q in range(n + 1):
+                o, s = owner_slot(q)
+                assert 0 <= o < P and 0 <= s < lay.local_len and (o, s) not in seen
+                seen.add((o, s))
+            idx = rng.permutation(n + 1).astype(np.uint32)
+            val = rng.integers(0, 2 ** 32, n + 1, dtype=np.uint64).astype(np.uint32)
+            skip = rng.random(n + 1) < 0.1
+            idx_in = np.where(skip, np.uint32(0xFFFFFFFF), idx).astype(np.uint32)
+            rc = L.sab200_dist_scatter_p2p(idx_in.ctypes.data, val.ctypes.data, n + 1, lay.width, P, lay.shift,
+                                           ptrs.ctypes.data_as(C.c_void_p), 0)
+            assert rc == 0
+            model = np.full(n + 1, 0xDEADBEEF, dtype=np.uint32)
+            model[idx[~skip]] = val[~skip]
+            for q in range(n + 1):
+                o, s = owner_slot(q)
+                assert peers[o][s] == model[q], (n, P, kind, q)
+            h = 3
+            m = max(1, n - h)
+            pos = rng.integers(0, n + 1 - h, m, dtype=np.uint64).astype(np.uint32)
+            r1 = rng.integers(0, 2 ** 32, m, dtype=np.uint64).astype(np.uint32)
+            key64 = np.zeros(m, dtype=np.uint64)
+            rc = L.sab200_dist_gather_p2p(r1.ctypes.data, pos.ctypes.data, m, h, lay.width, P, lay.shift,
+                                          ptrs.ctypes.data_as(C.c_void_p), key64.ctypes.data, 0)
+            assert rc == 0
+            exp = (r1.astype(np.uint64) << np.uint64(32)) | model[pos.astype(np.int64) + h].astype(np.uint64)
+            assert np.array_equal(key64, exp), (n, P, kind)
