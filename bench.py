@@ -159,7 +159,7 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": "sa_construction_throughput", "value": round(v, 3), "unit": "MB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
         "config": {"workload": desc, "sample": sample},
         "cpu_baseline": {"value": round(v, 3), "unit": "MB/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "oracle SA-IS port; reference libdivsufsort (single thread) is not buildable here"},
@@ -293,7 +293,7 @@ def main():
         print(json.dumps({
             "metric": "sa_construction_throughput", "value": round(value, 2), "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8 text / u64 keys / u32 ranks", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8 text / u64 keys / u32 ranks", "data": "synthetic",
             "config": {"workload": desc if not args.n_mib else "%s at %d MiB" % (args.workload, args.n_mib),
                        "text_bytes": n, "per_gpu": "independent replica (one text per rank)" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (no flush needed)" if n > (126 << 20) else "working set 36n bytes > L2",
