@@ -132,3 +132,42 @@ def test_small_alphabets_and_periodic(oracle):
             assert sa.tolist() == sorted(range(n + 1), key=lambda i: s[i:])
     s = (b"abcab" * 400)[:1999]
     assert oracle.check_integrity(s, oracle.saca(s))
+
+
+def _pack_model(sa):
+    """Independent pure-Python model of the `pack` byte layout (bincode fixint little-endian
+    header "SA4x" + length u32 + data length u64, then BitPacker4x blocks: value j of a 128-value block lives
+    in 32-bit lane j % 4 at bit (j // 4) * bits of that lane's LSB-first bit stream, the four lanes interleaved
+    word by word; trailing zero bytes of a partial last block are dropped)."""
+    import struct
+    n = len(sa)
+    bits = 0 if n <= 1 else (n - 1).bit_length()
+    data = bytearray()
+    for b0 in range(0, n, 128):
+        blk = list(sa[b0:b0 + 128]) + [0] * (128 - len(sa[b0:b0 + 128]))
+        lanes = [0, 0, 0, 0]
+        for j, v in enumerate(blk):
+            lanes[j % 4] |= (int(v) & ((1 << bits) - 1)) << ((j // 4) * bits)
+        out = bytearray()
+        for w in range(bits):
+            for lane in range(4):
+                out += struct.pack("<I", (lanes[lane] >> (32 * w)) & 0xFFFFFFFF)
+        if b0 + 128 > n:  # partial block
+            while out and out[-1] == 0:
+                out.pop()
+        data += out
+    return struct.pack("<IIQ", 0x78344153, n, len(data)) + bytes(data)
+
+
+def test_pack_layout_against_python_model(oracle):
+    # worked example of SURVEY.md 5.4 ("banana"), then random arrays around the block size
+    assert oracle.pack(oracle.saca(b"banana")).hex() == "53413478070000000d0000000000000006000000250000001300000001"
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 2, 3, 127, 128, 129, 255, 256, 257, 1000, 4096):
+        sa = rng.permutation(n).astype(np.uint32) if n else np.zeros(0, dtype=np.uint32)
+        b = oracle.pack(sa)
+        assert b == _pack_model(sa), n
+        assert np.array_equal(oracle.unpack(b), sa)
+    for bad in (b"", b"SA4x", _pack_model([1, 0])[:-1], b"XXXX" + _pack_model([1, 0])[4:]):
+        with pytest.raises(ValueError):
+            oracle.unpack(bad)
