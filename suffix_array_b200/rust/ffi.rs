@@ -18,6 +18,10 @@ extern "C" {
     pub fn sab200_search_all_batch(ix: *mut Sab200Index, pats: *const u8, offs: *const u64, np: u64, lo: *mut u32, hi: *mut u32) -> i32;
     pub fn sab200_contains_batch(ix: *mut Sab200Index, pats: *const u8, offs: *const u64, np: u64, out: *mut u8) -> i32;
     pub fn sab200_search_lcp_batch(ix: *mut Sab200Index, pats: *const u8, offs: *const u64, np: u64, start: *mut u32, end: *mut u32) -> i32;
+    // feature "pack": GPU forms of PackedSuffixArray::from_sa + dump_bytes / load_bytes + into_sa (src/packed_sa.rs)
+    pub fn sab200_pack_bound(sa_len: u64) -> u64;
+    pub fn sab200_pack(sa: *const u32, sa_len: u64, out: *mut u8, out_cap: u64, out_len: *mut u64) -> i32;
+    pub fn sab200_unpack(bytes: *const u8, nbytes: u64, sa: *mut u32, sa_cap: u64, sa_len: *mut u64) -> i32;
     pub fn sab200_last_error() -> *const c_char;
     pub fn sab200_shutdown();
 }
