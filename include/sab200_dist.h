@@ -97,6 +97,21 @@ int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint6
                            uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
                            uint32_t* d_upd_r, uint32_t* d_set_pos, uint64_t* n_kept, int32_t device);
 
+/* Lazy inverse suffix array, distributed (block layout only; SAB_DIST_LAZY=1 in dist.py): only the ranks of
+ * active suffixes are stored at their owners, rank[] starts 0xFFFFFFFF (EMPTY).  At the owner, after
+ * sab200_dist_gather: lazy_collect compacts the requests answered EMPTY into (key of suffix d_q[t] + h packed
+ * from the text shard, t); the keys travel to the GPU whose slice holds them (sab200_dist_partition_keys +
+ * all_to_all), lower_bound there turns each into its rank (slice offset + index in the sorted keys;
+ * 0xFFFFFFFF if absent, which would be a bug), and lazy_fill stores the returned ranks into the answers and
+ * into rank[] (memoised). */
+int32_t sab200_dist_lazy_collect(const uint32_t* d_q, const uint32_t* d_ans, uint64_t count, uint32_t h, uint64_t shard_lo,
+                                 const uint8_t* d_text, uint64_t n, const uint16_t* lut256, int32_t b, int32_t k,
+                                 uint64_t* d_keys_out, uint32_t* d_slot_out, uint64_t* n_unresolved, int32_t device);
+int32_t sab200_dist_lower_bound(const uint64_t* d_sorted_keys, uint64_t R, const uint64_t* d_keys, uint64_t count,
+                                uint32_t sa_off, uint32_t* d_rank_out, int32_t device);
+int32_t sab200_dist_lazy_fill(const uint32_t* d_slot, const uint32_t* d_rank, uint64_t count, const uint32_t* d_q, uint32_t h,
+                              uint32_t lo, uint32_t* d_ans, uint32_t* d_rank_local, int32_t device);
+
 /* Peer-to-peer form of the round exchanges (NVLink): peer_rank_ptrs (host array of P device addresses)
  * are the rank[] arrays of all GPUs mapped into this process (symmetric memory; layout as above).
  *   gather:  d_key64[t] = (d_r1[t] << 32) | rank[d_idx[t] + h], loaded from the owner GPU

@@ -296,6 +296,100 @@ extern "C" int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d
     return SAB_OK;
 }
 
+// ------------------------------------------------------------------ lazy inverse suffix array, distributed
+// As on one GPU (sab_saca.cuh, step 5) only the ranks of ACTIVE suffixes are stored at their owners; rank[]
+// starts EMPTY.  A request that finds EMPTY at the owner concerns a suffix that was unique after the initial
+// sort: the owner re-packs its key from its text shard (lazy_collect), the key travels to the GPU whose
+// slice holds it (same splitters as the key exchange), that GPU finds it in its sorted keys (lower_bound:
+// rank = slice offset + index) and the rank travels back to be stored and answered (lazy_fill).
+__global__ void __launch_bounds__(256)
+dist_lazy_collect_kernel(const u32* __restrict__ q, const u32* __restrict__ ans, u64 count, u32 h, u64 shard_lo,
+                         const u8* __restrict__ text, u64 n_rel, const u16* __restrict__ lut, u32 base, int k,
+                         u64* __restrict__ keys_out, u32* __restrict__ slot_out, u32* __restrict__ counter) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count || ans[t] != 0xffffffffu) return;
+    const u32 p = atomicAdd(counter, 1u);
+    keys_out[p] = pack_key_at(text, n_rel, lut, base, k, (u64)q[t] + h - shard_lo);
+    slot_out[p] = (u32)t;
+}
+__global__ void __launch_bounds__(256)
+dist_lower_bound_kernel(const u64* __restrict__ sorted, u64 R, const u64* __restrict__ keys, u64 count, u32 sa_off,
+                        u32* __restrict__ rank_out) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const u64 key = keys[t];
+    u64 lo = 0, hi = R;
+    while (lo < hi) {
+        const u64 mid = lo + (hi - lo) / 2;
+        if (sorted[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    // the key of a suffix that was unique after the initial sort is present exactly once
+    rank_out[t] = (lo < R && sorted[lo] == key) ? sa_off + (u32)lo : 0xffffffffu;
+}
+__global__ void __launch_bounds__(256)
+dist_lazy_fill_kernel(const u32* __restrict__ slot, const u32* __restrict__ rank, u64 count, const u32* __restrict__ q, u32 h,
+                      u32 lo, u32* __restrict__ ans, u32* __restrict__ rank_local) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const u32 s = slot[t], r = rank[t];
+    ans[s] = r;
+    rank_local[(u64)q[s] + h - lo] = r;  // memoised: the next request for this position is answered directly
+}
+
+extern "C" int32_t sab200_dist_lazy_collect(const uint32_t* d_q, const uint32_t* d_ans, uint64_t count, uint32_t h,
+                                            uint64_t shard_lo, const uint8_t* d_text, uint64_t n, const uint16_t* lut256,
+                                            int32_t b, int32_t k, uint64_t* d_keys_out, uint32_t* d_slot_out,
+                                            uint64_t* n_unresolved, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (!n_unresolved || !lut256 || shard_lo > n || b < 2 || k < 1 || k > 64) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *n_unresolved = 0;
+    if (count == 0) return SAB_OK;
+    cudaStream_t st = c->stream;
+    u16* d_lut = (u16*)(c->d_counters + 16 + 256);
+    memcpy(c->h_small + 384, lut256, 256 * sizeof(u16));
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, 256 * sizeof(u16), cudaMemcpyHostToDevice, st));
+    u32* d_cnt = c->d_counters + 12;
+    SAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(u32), st));
+    SAB_LAUNCH(dist_lazy_collect_kernel, (unsigned)div_up64(count, 256), 256, 0, st, d_q, d_ans, count, h, shard_lo, d_text,
+               n - shard_lo, (const u16*)d_lut, (u32)b, (int)k, d_keys_out, d_slot_out, d_cnt);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 12, d_cnt, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    *n_unresolved = c->h_small[12];
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_dist_lower_bound(const uint64_t* d_sorted_keys, uint64_t R, const uint64_t* d_keys, uint64_t count,
+                                           uint32_t sa_off, uint32_t* d_rank_out, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (count) {
+        SAB_LAUNCH(dist_lower_bound_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_sorted_keys, R, d_keys, count,
+                   sa_off, d_rank_out);
+        SAB_LAUNCH_CHECK();
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
+extern "C" int32_t sab200_dist_lazy_fill(const uint32_t* d_slot, const uint32_t* d_rank, uint64_t count, const uint32_t* d_q,
+                                         uint32_t h, uint32_t lo, uint32_t* d_ans, uint32_t* d_rank_local, int32_t device) {
+    SabContext* c = sab_dist_ctx(device);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (count) {
+        SAB_LAUNCH(dist_lazy_fill_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_slot, d_rank, count, d_q, h, lo,
+                   d_ans, d_rank_local);
+        SAB_LAUNCH_CHECK();
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+
 // Bracket a multi-GPU construction on this rank: begin() clears the counters (and arms the per-launch
 // events when profiling is on); end() collects them into the record sab200_get_stats() returns.
 extern "C" int32_t sab200_dist_begin(int32_t device) {

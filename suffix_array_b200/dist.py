@@ -40,6 +40,12 @@ REBALANCE_MIN_RECORDS = int(os.environ.get("SAB_REBALANCE_MIN", 1 << 20))
 # (profiles/r01_multi_gpu.md); it is exercised by the gloo tests and becomes the default once its
 # peer-to-peer kernels have been validated on GPUs.
 RANK_LAYOUT = os.environ.get("SAB_RANK_LAYOUT", "block")
+# "1": lazy inverse suffix array (block layout): only active ranks travel to their owners; a request that
+# finds EMPTY is resolved through the key of the suffix (see include/sab200_dist.h).  Pays when few suffixes
+# stay active after the initial sort (1 GiB DNA-like text: 5 %; all ranks to owners is a third of the 2-GPU
+# step).  Exercised by the gloo tests; not measured on GPUs yet, so off by default.
+LAZY_ISA = os.environ.get("SAB_DIST_LAZY", "0") == "1"
+LAZY_MAX_ACTIVE = float(os.environ.get("SAB_DIST_LAZY_MAX_ACTIVE", 0.25))  # lazy while at most this share of the suffixes is active
 
 
 class RankLayout:
@@ -90,6 +96,9 @@ def _bind(L):
         "sab200_dist_make_keys": [vp, vp, u64, vp, i32],
         "sab200_dist_rerank": [vp, vp, u64, u32, vp, vp, vp, vp, vp, vp, C.POINTER(u64), i32],
         "sab200_dist_partition_slices": [vp, vp, u64, vp, i32, vp, vp, vp, i32],
+        "sab200_dist_lazy_collect": [vp, vp, u64, u32, u64, vp, u64, vp, i32, i32, vp, vp, C.POINTER(u64), i32],
+        "sab200_dist_lower_bound": [vp, u64, vp, u64, u32, vp, i32],
+        "sab200_dist_lazy_fill": [vp, vp, u64, vp, u32, u32, vp, vp, i32],
         "sab200_dist_begin": [i32],
         "sab200_dist_end": [i32],
         "sab200_dist_gather_p2p": [vp, vp, u64, u32, u32, i32, i32, vp, vp, i32],
@@ -117,6 +126,7 @@ class _Ctx:
         self.collectives = 0
         self.phase_ms = {}
         self.tracing = os.environ.get("SAB_DIST_TRACE", "0") == "1"
+        self.resolved_empty = 0
         self._t = None
 
     def mark(self, name):
@@ -283,6 +293,31 @@ def _rebalance(cx, act_r1, act_idx, m):
     return r1, idx, r1.numel(), True
 
 
+def _resolve_empty(cx, q, ans, h, lo, d_text, n, lut, b, k, splitters, sorted_keys, R, sa_off, rank_local):
+    """Lazy inverse suffix array: the requests of this round that found EMPTY at this owner are resolved
+    through their keys (owner -> GPU holding the key -> owner) and memoised.  Collective: every rank calls it."""
+    cnt_q = q.numel()
+    keys_u = cx.empty(cnt_q, torch.int64)
+    slot_u = cx.empty(cnt_q, torch.int32)
+    nu = C.c_uint64()
+    cx.call("sab200_dist_lazy_collect", _p(q), _p(ans), cnt_q, h, lo, _p(d_text), n, lut.ctypes.data_as(C.c_void_p), b, k,
+            _p(keys_u), _p(slot_u), C.byref(nu), cx.dev)
+    nu = nu.value
+    kp = cx.empty(nu, torch.int64)
+    sp = cx.empty(nu, torch.int32)
+    cnt = np.zeros(cx.P, dtype=np.uint64)
+    cx.call("sab200_dist_partition_keys", _p(keys_u), _p(slot_u), nu, splitters.ctypes.data_as(C.c_void_p), cx.P - 1, _p(kp), _p(sp),
+            cnt.ctypes.data_as(C.c_void_p), cx.dev)
+    send = [int(x) for x in cnt]
+    recv = cx.exchange_counts(send)
+    kq = cx.all_to_all(kp, send, recv)
+    rk = cx.empty(kq.numel(), torch.int32)
+    cx.call("sab200_dist_lower_bound", _p(sorted_keys), R, _p(kq), kq.numel(), sa_off, _p(rk), cx.dev)
+    back = cx.all_to_all(rk, recv, send)
+    cx.call("sab200_dist_lazy_fill", _p(sp), _p(back), nu, _p(q), h, lo, _p(ans), _p(rank_local), cx.dev)
+    cx.resolved_empty += nu
+
+
 def _send_sa(cx, pos, idx, count, starts, sa_off, sa_local):
     """sa[pos[t]] = idx[t] on the GPU whose slice holds SA position pos[t] (entries with pos = 0xFFFFFFFF are dropped)."""
     kp = cx.empty(count, torch.int32)
@@ -432,18 +467,36 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
                                       C.byref(m), cx.dev)
     m = m.value
     cx.mark("init_ranks")
-    # 5. every rank travels to the owner of its text position
+    # 5. ranks travel to the owners of their text positions: all of them, or (lazy) only the active ones
+    lazy = False
+    if LAZY_ISA and lay.kind == "block" and n > 0:
+        tot0 = torch.tensor([m], dtype=torch.int64, device=cx.device)
+        dist.all_reduce(tot0, group=cx.group)
+        cx.collectives += 1
+        lazy = int(tot0.item()) <= LAZY_MAX_ACTIVE * n
+    src_idx, src_rank, src_cnt = (act_idx, act_r1, m) if lazy else (vs, rank_seq, R)
     if use_p2p:
-        rank_local.zero_()  # slot of position n (the empty suffix) must read 0
+        if lazy:
+            rank_local.fill_(-1)  # EMPTY
+        else:
+            rank_local.zero_()
         _barrier(cx)        # nobody stores into a block that is still being cleared
         if B <= P2P_MAX_RECORDS:
-            cx.call("sab200_dist_scatter_p2p", _p(vs), _p(rank_seq), R, lay.width, P, lay.shift, peer_arg, cx.dev)
+            cx.call("sab200_dist_scatter_p2p", _p(src_idx), _p(src_rank), src_cnt, lay.width, P, lay.shift, peer_arg, cx.dev)
         else:
-            _send_ranks(cx, vs, rank_seq, R, lay, lo, rank_local)
+            _send_ranks(cx, src_idx, src_rank, src_cnt, lay, lo, rank_local)
     else:
-        rank_local = torch.zeros(lay.local_len, dtype=torch.int32, device=cx.device)  # the slot of position n reads 0
-        _send_ranks(cx, vs, rank_seq, R, lay, lo, rank_local)
-    del ks, vs, k0, k1, v0, v1, rank_seq
+        rank_local = torch.full((lay.local_len,), -1 if lazy else 0, dtype=torch.int32, device=cx.device)
+        _send_ranks(cx, src_idx, src_rank, src_cnt, lay, lo, rank_local)
+    if lazy:
+        # the empty suffix (position n) has rank 0; every other EMPTY slot is resolved on demand
+        o_n = min(n // lay.width, P - 1)
+        if rank == o_n:
+            rank_local[n - o_n * lay.width] = 0
+        if use_p2p:
+            _barrier(cx)
+        sorted_keys = ks  # this rank's slice of the sorted keys answers the key look-ups of the rounds
+    del src_idx, src_rank, ks, vs, k0, k1, v0, v1, rank_seq
     cx.mark("ranks_to_owners")
     # 6. doubling rounds
     rank_bits = max(1, int(n + 1).bit_length())
@@ -466,7 +519,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
             raise RuntimeError("prefix doubling did not converge")
         cx.trace("rounds/count")
         key64 = cx.empty(m, torch.int64)
-        p2p_round = use_p2p and tot <= P2P_MAX_RECORDS * P  # same decision on every rank
+        p2p_round = use_p2p and tot <= P2P_MAX_RECORDS * P and not lazy  # same decision on every rank
         if p2p_round:
             # the all_reduce above ordered every rank's previous stores before these loads
             cx.call("sab200_dist_gather_p2p", _p(cur_r1), _p(cur_idx), m, h, lay.width, P, lay.shift, peer_arg, _p(key64), cx.dev)
@@ -481,6 +534,9 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
             ans = cx.empty(q.numel(), torch.int32)
             cx.call("sab200_dist_gather", _p(q), q.numel(), h, lo, lay.width, P, lay.shift, _p(rank_local), _p(ans), cx.dev)
             cx.trace("rounds/gather")
+            if lazy:
+                _resolve_empty(cx, q, ans, h, lo, d_text, n, lut, b, k, splitters, sorted_keys, R, sa_off, rank_local)
+                cx.trace("rounds/resolve_empty")
             r2 = cx.all_to_all(ans, recv, send)
             cx.trace("rounds/send_answers")
             cx.call("sab200_dist_make_keys", _p(rpart), _p(r2), m, _p(key64), cx.dev)
@@ -523,6 +579,7 @@ def dist_saca(shard, n, device, group=None, stats=None, exchange="auto"):
         stats.update({"rounds": rounds, "active": active, "slice": R, "sa_off": sa_off, "symbols_per_key": k,
                       "bits_per_symbol": b, "all_to_all_bytes": cx.a2a_bytes, "collectives": cx.collectives,
                       "exchange": "p2p" if use_p2p else "collective", "rebalanced": rebalanced, "rank_layout": lay.kind,
+                      "lazy_isa": lazy, "resolved_empty": cx.resolved_empty,
                       "phase_ms": {k_: round(v_, 2) for k_, v_ in cx.phase_ms.items()},
                       "wall_ms": round((time.perf_counter() - t_enter) * 1e3, 2)})
     return sa_local, sa_off

@@ -50,9 +50,9 @@ def main():
         if rank == 0:
             exp = oracle.saca(t)
             good = bool(np.array_equal(full, exp))
-            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d exchange=%s rebalanced=%s layout=%s" % (
-                n, world, st["rounds"], good, st["all_to_all_bytes"], st["exchange"], st.get("rebalanced"), st.get("rank_layout")),
-                  flush=True)
+            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d exchange=%s rebalanced=%s layout=%s lazy=%s resolved=%d " % (
+                n, world, st["rounds"], good, st["all_to_all_bytes"], st["exchange"], st.get("rebalanced"), st.get("rank_layout"),
+                st.get("lazy_isa"), st.get("resolved_empty", 0)), flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.broadcast(flag, 0)
