@@ -12,19 +12,24 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("world,port,exchange,layout", [(2, 29621, "p2p", "block"), (2, 29623, "nccl", "block"),
                                                         (2, 29624, "mixed", "block"), (4, 29622, "auto", "block"),
-                                                        (2, 29625, "mixed", "cyclic"), (2, 29626, "p2p", "cyclic")])
+                                                        (2, 29625, "mixed", "cyclic"), (2, 29626, "p2p", "cyclic"),
+                                                        (2, 29627, "nccl", "lazy"), (2, 29628, "p2p", "lazy")])
 def test_dist_construction_nccl(gpu_lib, world, port, exchange, layout):
     if gpu_lib.sab200_device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
+    lazy = layout == "lazy"  # distributed lazy inverse suffix array (block layout)
+    layout = "block" if lazy else layout
     env = dict(os.environ, SAB_DIST_BACKEND="nccl", SAB_DIST_EXCHANGE="p2p" if exchange == "mixed" else exchange,
-               SAB_RANK_LAYOUT=layout)
+               SAB_RANK_LAYOUT=layout, SAB_DIST_LAZY="1" if lazy else "0")
     if exchange == "mixed":  # large rounds through all_to_all, small ones through peer loads / stores
         env["SAB_P2P_MAX_RECORDS"] = "20000"
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("slices_ok=True") == 16, out.stdout
     assert out.stdout.count("layout=" + layout) == 16, out.stdout
+    if lazy:
+        assert "lazy=True" in out.stdout, out.stdout
     if exchange in ("p2p", "mixed"):
         assert "exchange=p2p" in out.stdout
