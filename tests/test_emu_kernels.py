@@ -133,3 +133,32 @@ def test_emu_peer_rank_kernels_both_layouts(emu_lib):
             assert rc == 0
             exp = (r1.astype(np.uint64) << np.uint64(32)) | model[pos.astype(np.int64) + h].astype(np.uint64)
             assert np.array_equal(key64, exp), (n, P, kind)
+
+
+def test_emu_radix_sort_direct(emu_lib):
+    """The LSD radix sort on its own (through sab200_dist_sort_pairs): stable order of (key, payload) pairs
+    against numpy for sizes around the tile (4096) and look-back group (8 tiles) limits and for skewed,
+    constant and wide digits -- the two-level look-back sees complete, partial and single groups."""
+    import ctypes as C
+    from suffix_array_b200 import dist as sdist
+    L = sdist._bind(emu_lib)
+    rng = np.random.default_rng(123)
+    cases = []
+    for n in (1, 31, 4095, 4096, 4097, 8 * 4096, 8 * 4096 + 1, 9 * 4096 - 1, 70000, 17 * 4096):
+        cases.append((n, 64, rng.integers(0, 2 ** 63, n, dtype=np.int64).astype(np.uint64) * np.uint64(2)
+                      + rng.integers(0, 2, n, dtype=np.int64).astype(np.uint64)))
+    cases.append((50000, 17, rng.integers(0, 2 ** 17, 50000, dtype=np.int64).astype(np.uint64)))          # 3 passes, top one partial
+    cases.append((40000, 40, (rng.integers(0, 3, 40000, dtype=np.int64).astype(np.uint64) << np.uint64(32))
+                  | rng.integers(0, 5, 40000, dtype=np.int64).astype(np.uint64)))                          # few distinct digits
+    cases.append((33000, 64, np.full(33000, 0x0123456789ABCDEF, dtype=np.uint64)))                        # every pass is a no-op
+    cases.append((36000, 48, np.sort(rng.integers(0, 2 ** 48, 36000, dtype=np.int64).astype(np.uint64))[::-1].copy()))  # reversed
+    for n, bits, keys in cases:
+        vals = rng.permutation(n).astype(np.uint32)
+        k0, v0 = keys.copy(), vals.copy()
+        k1, v1 = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
+        which = L.sab200_dist_sort_pairs(k0.ctypes.data, k1.ctypes.data, v0.ctypes.data, v1.ctypes.data, n, bits, 0)
+        assert which in (0, 1), which
+        ks, vs = (k0, v0) if which == 0 else (k1, v1)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(ks, keys[order]), (n, bits)
+        assert np.array_equal(vs, vals[order]), (n, bits)
