@@ -162,3 +162,28 @@ def test_emu_radix_sort_direct(emu_lib):
         order = np.argsort(keys, kind="stable")
         assert np.array_equal(ks, keys[order]), (n, bits)
         assert np.array_equal(vs, vals[order]), (n, bits)
+
+
+def test_argument_errors(emu_lib):
+    """Error behaviour at the boundary: bad sizes / null pointers return SAB200_ERR_ARGS (-1) with
+    a message instead of the reference's panics (src/saca.rs:10-11); nothing is dereferenced."""
+    import ctypes as C
+    L = emu_lib
+    buf = np.zeros(16, dtype=np.uint32)
+    txt = np.zeros(16, dtype=np.uint8)
+    too_long = 0xFFFFFFFF  # MAX_LENGTH + 1
+    assert L.sab200_saca(txt.ctypes.data, too_long, buf.ctypes.data, 1) == -1
+    assert b"MAX_LENGTH" in L.sab200_last_error() or L.sab200_last_error()
+    assert L.sab200_saca(txt.ctypes.data, 4, None, 1) == -1
+    assert L.sab200_saca(None, 4, buf.ctypes.data, 1) == -1
+    assert L.sab200_saca(txt.ctypes.data, 4, buf.ctypes.data, 2) == -1      # multi-GPU = one process per GPU (sab200_dist.h)
+    assert L.sab200_enable_buckets(txt.ctypes.data, too_long, buf.ctypes.data) == -1
+    assert L.sab200_check(txt.ctypes.data, too_long, buf.ctypes.data, 5) == -1
+    assert not L.sab200_index_create(txt.ctypes.data, 4, None, None, 1)
+    n_out = C.c_uint64()
+    assert L.sab200_pack(buf.ctypes.data, 4, txt.ctypes.data, 3, C.byref(n_out)) == -1        # output buffer too small
+    assert L.sab200_unpack(txt.ctypes.data, 8, buf.ctypes.data, 16, C.byref(n_out)) == -1     # truncated header
+    # the empty text is legal everywhere (src/tests.rs strategies include it)
+    sa0 = np.full(1, 7, dtype=np.uint32)
+    assert L.sab200_saca(None, 0, sa0.ctypes.data, 1) == 0 and sa0[0] == 0
+    assert L.sab200_check(None, 0, sa0.ctypes.data, 1) == 1
