@@ -51,3 +51,9 @@ def emu_backend(emu_lib, monkeypatch):
 def gpu_lib():
     from suffix_array_b200 import _lib
     return _lib.require_gpu()
+
+
+def pytest_collection_modifyitems(config, items):
+    """The multi-GPU cases run last: with `-x` a failure there must not keep the single-GPU parity tests
+    (the first gate) from running."""
+    items.sort(key=lambda it: 1 if "test_gpu_multi" in it.nodeid else 0)  # stable: the rest keeps its order

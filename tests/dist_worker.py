@@ -19,7 +19,7 @@ def main():
     from suffix_array_b200 import dist as sdist
     from oracle import oracle
     rng = np.random.default_rng(1234)
-    if backend == "nccl":  # real GPUs, real library (tests/test_gpu_dist.py)
+    if backend == "nccl":  # real GPUs, real library (tests/test_gpu_multi.py)
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
