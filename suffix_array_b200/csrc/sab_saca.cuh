@@ -40,10 +40,12 @@
 #else
 #define SAB_FILTER_MIN ((u64)1 << 20)
 #endif
+#ifndef SAB_ACTIVE_COST
 #ifdef SAB_EMU
 #define SAB_ACTIVE_COST 30.0  // emulator runs are tiny: keep the doubling rounds exercised
 #else
 #define SAB_ACTIVE_COST 300.0
+#endif
 #endif
 
 // ------------------------------------------------------------------ 1. alphabet
