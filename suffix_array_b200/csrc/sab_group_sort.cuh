@@ -147,7 +147,9 @@ struct GroupSortSpare {
     u64 cap;
 };
 
-// Sorts the cnt records of (sb.k[0], sb.v[0]) -- grouped by the high key word -- by the full key.
+// Sorts the cnt records of (sb.k[0], sb.v[0]) -- grouped by the high key word, the groups in ASCENDING order of
+// that word (the scatter-back pairs the j-th radix-sorted large-group record with the j-th recorded position) --
+// by the full key.
 // Returns 1 with the result in (sb.k[1], sb.v[1]) and sb.cur = 1; returns 0 with the input untouched when
 // more records than sp.cap belong to big groups (the caller falls back to the radix sort); < 0 on error.
 // *nbig_out = number of records that needed the radix sort.

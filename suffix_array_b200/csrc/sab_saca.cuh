@@ -453,6 +453,11 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     // the split filter (5c) pays off while few groups split: repetitive texts, early rounds
     bool filter_on = (z.sorted_keys == nullptr) && m >= SAB_FILTER_MIN;
     bool group_sort_on = SAB_GROUP_SORT != 0;
+    // The active list leaves init_ranks ascending in r1.  A round of the split filter parks the unsplit
+    // groups in front of the re-ranked ones, so the next list is two ascending runs: groups stay contiguous
+    // (all the scan kernels need) but the list is no longer monotone -- and sab_group_sort returns the
+    // radix-sorted records of large groups to their positions in LIST order, which needs a monotone list.
+    bool list_sorted = true;
     while (m > 0) {
         ++round;
         if (round >= SAB_MAX_ROUNDS || h > n) {
@@ -498,7 +503,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             // 5d. small groups are ordered in one sweep; the spare buffers for the records of big groups are
             // the unused tails of the round buffers (keys, payloads) and of r1buf (positions)
             int sorted = 0;
-            if (group_sort_on) {
+            if (group_sort_on && list_sorted) {
                 const u64 used = sab_align_up(n_sort, 64);
                 const u64 cap_keys = key_cap > used ? key_cap - used : 0;
                 const u64 cap_vals = n + 8 > n_stay + used ? n + 8 - n_stay - used : 0;
@@ -535,6 +540,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             if (sb.cur != 0 && kept > 0)  // the survivors were written to the other buffer: append them to the parked ones
                 SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1] + n_stay, rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
         }
+        // parked records first, then the survivors of the sort (ascending either way it was sorted)
+        list_sorted = n_stay == 0;
         rb.cur ^= 1;
         m = n_stay + kept;
         S.active[round] = m;

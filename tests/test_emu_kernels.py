@@ -77,6 +77,9 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
         pc.check_construction(oracle, t)
         st = _lib.last_stats()
         assert st["group_sort_records"] > 0, (r, blk, st)
+    # split filter + in-group sort: parked groups make the next list two ascending runs; the large-group records
+    # must then go through the full radix sort (regression: they were returned to positions of other groups)
+    pc.check_construction(oracle, gen.repetitive(9518, block=2180, mut_rate=0.01))
     # small and large groups interleaved in one list
     a = np.tile(rng.integers(0, 4, 70, dtype=np.uint8), 40)
     b = np.tile(rng.integers(0, 4, 400, dtype=np.uint8), 3)
