@@ -69,7 +69,7 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
     """Rounds whose groups sit right at the limits of group_sort_kernel: a random block repeated r times gives
     groups of r records (r = 32: ordered in shared memory, r = 33: radix path), lists longer than one
     2048-record tile (groups cut by tile borders), and mixtures of both kinds."""
-    from suffix_array_b200 import _lib
+    from suffix_array_b200 import _lib, gen
     rng = np.random.default_rng(77)
     for r, blk in ((31, 97), (32, 90), (33, 90), (34, 61), (2, 1500), (3, 1100)):
         block = rng.integers(0, 4, blk, dtype=np.uint8)
