@@ -2,9 +2,14 @@
 emulator of tests/emu (fibers; interleaved blocks, so the decoupled look-back takes both its
 PARTIAL and INCLUSIVE paths) and compared bit-exactly with the oracle.  These are NOT the parity
 gate -- that is tests/test_gpu_*.py on a B200 -- they keep the kernels honest where no GPU exists."""
+import os
+
 import numpy as np
+import pytest
 
 from tests import parity_cases as pc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_emu_golden_and_doctests(emu_backend, oracle, golden):
@@ -190,3 +195,43 @@ def test_argument_errors(emu_lib):
     sa0 = np.full(1, 7, dtype=np.uint32)
     assert L.sab200_saca(None, 0, sa0.ctypes.data, 1) == 0 and sa0[0] == 0
     assert L.sab200_check(None, 0, sa0.ctypes.data, 1) == 1
+
+
+def _random_text(rng):
+    """Texts with structure: runs, repeats with mutations, mixtures of unique and repetitive regions."""
+    from suffix_array_b200 import gen
+    kind = int(rng.integers(0, 6))
+    n = int(rng.integers(1, 40000))
+    if kind == 0:
+        return rng.integers(0, int(rng.integers(1, 6)), n, dtype=np.uint8)
+    if kind == 1:
+        return gen.dna_like(n)
+    if kind == 2:
+        return gen.repetitive(n, block=int(rng.integers(8, 3000)), mut_rate=float(rng.choice([0, 1e-3, 1e-2, 1e-1])))
+    if kind == 3:
+        return gen.mixed_range(max(n, 64), 0, max(n, 64))
+    if kind == 4:
+        a = rng.integers(0, 256, n // 2 + 1, dtype=np.uint8)
+        b = np.tile(rng.integers(97, 101, int(rng.integers(3, 90)), dtype=np.uint8), n // 50 + 2)
+        return np.concatenate([a, b, a[:n // 5]])
+    base = gen.repetitive(max(n, 100), block=int(rng.integers(50, 1500)), mut_rate=float(rng.choice([1e-3, 1e-2])))
+    return np.concatenate([base, gen.dna_like(max(n // 3, 10)), base[:n // 2]])
+
+
+@pytest.mark.parametrize("build", ["emu", "emu-prod"])
+def test_emu_randomized_construction(build, emu_lib, oracle, monkeypatch):
+    """Fixed-seed randomized constructions under both emulator builds (`emu-prod` = production cost-model
+    constant: few suffixes stay active after the initial sort, so the lazy inverse suffix array and the
+    in-group sort carry the rounds as they do on the GPU).  This pair found the split-filter / in-group-sort
+    ordering bug fixed in round 1."""
+    import ctypes
+    import subprocess
+    from suffix_array_b200 import _lib
+    lib = emu_lib
+    if build == "emu-prod":
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "suffix_array_b200", "csrc"), "emu-prod"], stdout=subprocess.DEVNULL)
+        lib = _lib._bind(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libsab200_emu_prod.so")))
+    monkeypatch.setattr(_lib, "_lib", lib)
+    rng = np.random.default_rng(2026)
+    for _ in range(16):
+        pc.check_construction(oracle, _random_text(rng))
