@@ -130,6 +130,19 @@ def test_baseline_shapes_16mib_bit_exact(gpu_lib, oracle):
         pc.check_construction(oracle, s)
 
 
+def test_filter_and_group_sort_rounds(gpu_lib, oracle):
+    # Repeats with 1 % / 3 % mutations: most suffixes stay active (eager inverse suffix array), the split
+    # filter parks unsplit groups while other large groups split, small groups go through the in-group sort.
+    # The CPU regression of this combination is tests/test_emu_kernels.py::test_emu_group_sort_boundaries.
+    from suffix_array_b200 import last_stats
+    n = 12 << 20
+    for block, mut in ((n * 10 // 44, 1e-2), (n // 3 + 17, 3e-2), (1 << 13, 1e-2)):  # groups of <= 5, <= 3, ~1500 records
+        s = gen.repetitive(n, block=block, mut_rate=mut)
+        sa = SuffixArray(s)
+        assert oracle.sufcheck(s, sa.sa), (block, mut, last_stats())
+        assert SuffixArray.from_parts(s, sa.sa) is not None
+
+
 def test_c1_uniform_64mib(gpu_lib, oracle):
     # BASELINE.json configs[0] at full size: linear-time verifiers on CPU and GPU
     s = gen.uniform_bytes(64 << 20)
