@@ -429,7 +429,7 @@ def bench_search(L, _lib, torch, dev, text, h_sa, n, npat=2_000_000):
     sa = h_sa.numpy().view(np.uint32)
     bkt = np.empty(_lib.BKT_LEN, dtype=np.uint32)
     _lib.check(L.sab200_enable_buckets(text.ctypes.data, n, bkt.ctypes.data), "sab200_enable_buckets")
-    ix = L.sab200_index_create(text.ctypes.data, n, sa.ctypes.data, bkt.ctypes.data, 1)
+    ix = L.sab200_index_create(text.ctypes.data, n, sa.ctypes.data, n + 1, bkt.ctypes.data, 1)
     if not ix:
         return {"error": L.sab200_last_error().decode()}
     pats, offs = gen.patterns(text, npat)

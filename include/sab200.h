@@ -94,10 +94,14 @@ int32_t sab200_check(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t 
 /* ---- batched queries -----------------------------------------------------------------------
  * A resident copy of (text, SA, optional bucket table) on `ngpus` GPUs (replicated; queries are
  * sharded across the replicas, no collective).  bkt_or_null = NULL means "buckets not enabled"
- * (get_bucket then returns the whole array, src/sa.rs:141-143).  Host buffers; copied, not kept. */
+ * (get_bucket then returns the whole array, src/sa.rs:141-143).  Host buffers; copied, not kept.
+ * sa_len must be n + 1 (NULL is returned otherwise): the safe mirrors can hold a stale array after the
+ * reference's set() quirk (src/sa.rs:30-33 keeps the old text), and a short one must not be over-read.
+ * Entries of `sa` larger than n (only reachable through unchecked_from_parts) are treated as the empty
+ * suffix by the kernels instead of indexing outside the text. */
 typedef struct sab200_index sab200_index;
-sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, const uint32_t* bkt_or_null,
-                                  int32_t ngpus);
+sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len,
+                                  const uint32_t* bkt_or_null, int32_t ngpus);
 void sab200_index_destroy(sab200_index* ix);
 
 /* Patterns are concatenated in `pats`; pattern q is pats[offs[q] .. offs[q+1]) (np+1 offsets).

@@ -195,7 +195,7 @@ class SuffixArray {
     SuffixArray(const std::uint8_t* s, std::size_t n, std::vector<std::uint32_t> sa) : s_(s), n_(n), sa_(std::move(sa)) {}
     sab200_index* index() {
         if (!ix_) {
-            ix_ = sab200_index_create(s_, n_, sa_.data(), has_bkt_ ? bkt_.data() : nullptr, ngpus_);
+            ix_ = sab200_index_create(s_, n_, sa_.data(), sa_.size(), has_bkt_ ? bkt_.data() : nullptr, ngpus_);
             if (!ix_) throw std::runtime_error(std::string("sab200_index_create: ") + sab200_last_error());
         }
         return ix_;

@@ -426,10 +426,15 @@ static int replica_init(SabReplica& r, int device, const u8* s, u64 n, const u32
     return SAB_OK;
 }
 
-extern "C" sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, const uint32_t* bkt_or_null,
-                                  int32_t ngpus) {
+extern "C" sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len,
+                                             const uint32_t* bkt_or_null, int32_t ngpus) {
     if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH || ngpus < 1 || ngpus > SAB_MAX_DEVICES) {
         sab_set_error("sab200_index_create: bad arguments");
+        return nullptr;
+    }
+    if (sa_len != n + 1) {
+        sab_set_error("sab200_index_create: the suffix array has %llu entries, the text needs %llu",
+                      (unsigned long long)sa_len, (unsigned long long)(n + 1));
         return nullptr;
     }
     if (ngpus > sab200_device_count()) {

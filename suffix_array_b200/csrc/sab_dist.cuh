@@ -117,7 +117,9 @@ extern "C" int32_t sab200_dist_pack(const uint8_t* d_text, uint64_t shard_lo, ui
     u16* d_lut = (u16*)(c->d_counters + 16 + 256);
     memcpy(c->h_small + 384, lut256, 256 * sizeof(u16));
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, 256 * sizeof(u16), cudaMemcpyHostToDevice, st));
-    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n - shard_lo, count,
+    // the shard buffer holds count + 64 bytes (halo) at most: never read past them (k <= 64 symbols per key)
+    const u64 avail = (n - shard_lo) < count + 64 ? (n - shard_lo) : count + 64;
+    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, avail, count,
                (const u16*)d_lut, (u32)b, (int)k, sab_pow_u64((u64)b, k - 1), d_keys);
     SAB_LAUNCH_CHECK();
     SAB_LAUNCH(iota_base_kernel, (unsigned)div_up64(count, 256), 256, 0, st, d_idx, count, (u32)shard_lo);

@@ -121,6 +121,19 @@ radix_scan_kernel(const u64* __restrict__ ghist, u64 n, int npass, u64* __restri
 #ifndef SAB_LB_DEPTH
 #define SAB_LB_DEPTH 4
 #endif
+// 1: a record goes to its shared-memory slot as soon as it is ranked (the slot does not depend on the
+// look-back), so the ranks[] array and one block barrier disappear and keys[] / vals[] die item by item:
+// no register spills under __launch_bounds__(256, 3).  0: rank all items, look back, then scatter (round 1).
+#ifndef SAB_FUSED_SCATTER
+#define SAB_FUSED_SCATTER 1
+#endif
+// 1: the ballot matching runs ONCE, in the histogram phase: the leader's atomic returns the first slot of the
+// digit group inside the warp's share of the bin, every lane keeps its 10-bit local rank, and after the block
+// scan the final slot is one shared-memory read (warp offset of the bin) + the local rank.  0: plain atomics
+// for the histogram, matching in the ranking phase.
+#ifndef SAB_RANK_ONCE
+#define SAB_RANK_ONCE 0
+#endif
 __device__ __forceinline__ u32 match_digit(u32 d) {
 #if SAB_MATCH_HW
     return __match_any_sync(SAB_FULL, d);
@@ -255,7 +268,9 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     // ---- load (warp-striped: item k of lane l is record w*WTILE + k*32 + l of the tile)
     KeyT keys[ITEMS];
     u32 vals[ITEMS];
+#if !SAB_FUSED_SCATTER
     u32 ranks[ITEMS];
+#endif
     const u32 wofs = w * WTILE + lane;
     const KeyT* kin = keys_in + tile_base + wofs;
     const u32* vin = IOTA_VAL ? nullptr : vals_in + tile_base + wofs;
@@ -281,8 +296,23 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     // ---- tile histogram first (plain shared-memory atomics, order irrelevant), so the tile's partial is
     // published a whole ranking phase before its successors look back: they never find it missing.
     u32* wh = s_whist + w * SAB_RADIX_BINS;
+#if SAB_RANK_ONCE
+    u32 lrank[(ITEMS + 1) / 2];  // two 16-bit local ranks (position inside the warp's share of the bin) per word
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 d = dop(keys[k]);
+        const u32 peers = match_digit(d);
+        const u32 leader = (u32)(__ffs((int)peers) - 1);
+        u32 old = 0;
+        if (lane == leader) old = atomicAdd(&wh[d], (u32)__popc(peers));  // same-address atomics of a warp retire in order
+        old = __shfl_sync(SAB_FULL, old, (int)leader) + (u32)__popc(peers & lanemask_lt());
+        if (k & 1) lrank[k / 2] |= old << 16;
+        else lrank[k / 2] = old;
+    }
+#else
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) atomicAdd(&wh[dop(keys[k])], 1u);
+#endif
     __syncthreads();
     u32 my_count = 0;
     u64* lb = lookback + (u64)tile * SAB_RADIX_BINS + tid;
@@ -345,10 +375,13 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         }
     }
     __syncthreads();
-    // ---- rank inside the warp (stable in (k, lane) order); ranks[k] = slot of the record in the sorted tile
+    // ---- rank inside the warp (stable in (k, lane) order): slot of the record in the sorted tile
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 d = dop(keys[k]);
+#if SAB_RANK_ONCE
+        const u32 pos = wh[d] + ((k & 1) ? (lrank[k / 2] >> 16) : (lrank[k / 2] & 0xffffu));
+#else
         const u32 peers = (SAB_HW_MATCH_EVERY > 0 && (k % (SAB_HW_MATCH_EVERY > 0 ? SAB_HW_MATCH_EVERY : 1)) == 0)
                               ? __match_any_sync(SAB_FULL, d)
                               : match_digit(d);
@@ -357,7 +390,14 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         u32 old = 0;
         if (lane == leader) old = atomicAdd(&wh[d], (u32)__popc(peers));
         old = __shfl_sync(SAB_FULL, old, (int)leader);
-        ranks[k] = old + (u32)__popc(peers & lanemask_lt());
+        const u32 pos = old + (u32)__popc(peers & lanemask_lt());
+#endif
+#if SAB_FUSED_SCATTER
+        s_keys[pos] = keys[k];
+        if (HAS_VAL) s_vals[pos] = vals[k];
+#else
+        ranks[k] = pos;
+#endif
     }
 #if SAB_LB_GROUP
     // ---- two-level look-back, one lane per bin: in-group tile partials and the first batch of group words
@@ -449,6 +489,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
     __syncthreads();
 
 #endif
+#if !SAB_FUSED_SCATTER
     // ---- scatter into shared memory in sorted order
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -457,6 +498,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         if (HAS_VAL) s_vals[pos] = vals[k];
     }
     __syncthreads();
+#endif
 
     // ---- coalesced write-out: consecutive shared slots of one bin are consecutive in global memory
     if (full) {

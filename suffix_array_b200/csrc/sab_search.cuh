@@ -119,7 +119,7 @@ struct SearchArgs {
 template <int G>
 __device__ __forceinline__ u64 group_compare(const SearchArgs& a, const u8* __restrict__ pat, u64 m, u64 p, u32 gmask,
                                              u32 gl, u32 gbase, u32 pw0, u32 pw1, u32* less_at) {
-    const u64 avail = a.n - p;
+    const u64 avail = p <= a.n ? a.n - p : 0;  // an entry beyond n (corrupt array) reads as the empty suffix
     const u64 L = m < avail ? m : avail;
     *less_at = 0;
     for (u64 c0 = 0; c0 < L || c0 == 0; c0 += 4 * G) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
         const u64 p = a.sa[mid];
         u32 less_at;
         const u64 d = group_compare<G>(a, pat, m, p, gmask, gl, gbase, pw0, pw1, &less_at);
-        const u64 avail = n - p;
+        const u64 avail = p <= n ? n - p : 0;
         const u64 L = m < avail ? m : avail;
         const bool suffix_less = (d < L) ? (less_at != 0) : (avail < m);
         if (suffix_less) i = mid + 1;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
             pb = a.sa[i];
             db = group_compare<G>(a, pat, m, pb, gmask, gl, gbase, pw0, pw1, &less_at);
         }
-        if (i < hi && db == m && n - pb == m) {  // Ok(i): a suffix equal to the pattern
+        if (i < hi && db == m && pb <= n && n - pb == m) {  // Ok(i): a suffix equal to the pattern
             st = pb;
             en = n;
         } else if (i > lo && i < hi) {

@@ -54,7 +54,9 @@ static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const 
     c->ticket_host += (u32)tiles;
     c->stats.radix_pass_launches += 1;
     c->stats.radix_pass_records += n;
-    c->stats.radix_pass_bytes += 2ull * (sizeof(KeyT) + sizeof(u32)) * n;
+    // algorithmic bytes: read K+V, write K+V -- the first pass of a sort generates its payload
+    // (iota) instead of reading it
+    c->stats.radix_pass_bytes += ((IOTA ? 1ull : 2ull) * sizeof(u32) + 2ull * sizeof(KeyT)) * n;
     c->stats.kernel_launches += 1;
     return SAB_OK;
 }

@@ -13,7 +13,7 @@ extern "C" {
     pub fn sab200_saca(s: *const u8, n: u64, sa: *mut u32, ngpus: i32) -> i32;
     pub fn sab200_enable_buckets(s: *const u8, n: u64, bkt: *mut u32) -> i32;
     pub fn sab200_check(s: *const u8, n: u64, sa: *const u32, sa_len: u64) -> i32;
-    pub fn sab200_index_create(s: *const u8, n: u64, sa: *const u32, bkt_or_null: *const u32, ngpus: i32) -> *mut Sab200Index;
+    pub fn sab200_index_create(s: *const u8, n: u64, sa: *const u32, sa_len: u64, bkt_or_null: *const u32, ngpus: i32) -> *mut Sab200Index;
     pub fn sab200_index_destroy(ix: *mut Sab200Index);
     pub fn sab200_search_all_batch(ix: *mut Sab200Index, pats: *const u8, offs: *const u64, np: u64, lo: *mut u32, hi: *mut u32) -> i32;
     pub fn sab200_contains_batch(ix: *mut Sab200Index, pats: *const u8, offs: *const u64, np: u64, out: *mut u8) -> i32;

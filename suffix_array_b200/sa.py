@@ -131,7 +131,7 @@ class SuffixArray:
     def _get_index(self):
         if self._index is None:
             L = _lib.require_gpu()
-            h = L.sab200_index_create(_ptr(self.s), self.s.size, self.sa.ctypes.data_as(C.c_void_p),
+            h = L.sab200_index_create(_ptr(self.s), self.s.size, self.sa.ctypes.data_as(C.c_void_p), self.sa.size,
                                       self.bkt.ctypes.data_as(C.c_void_p) if self.bkt is not None else None,
                                       self._ngpus)
             if not h:

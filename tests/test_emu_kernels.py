@@ -187,7 +187,7 @@ def test_argument_errors(emu_lib):
     assert L.sab200_saca(txt.ctypes.data, 4, buf.ctypes.data, 2) == -1      # multi-GPU = one process per GPU (sab200_dist.h)
     assert L.sab200_enable_buckets(txt.ctypes.data, too_long, buf.ctypes.data) == -1
     assert L.sab200_check(txt.ctypes.data, too_long, buf.ctypes.data, 5) == -1
-    assert not L.sab200_index_create(txt.ctypes.data, 4, None, None, 1)
+    assert not L.sab200_index_create(txt.ctypes.data, 4, None, 5, None, 1)
     n_out = C.c_uint64()
     assert L.sab200_pack(buf.ctypes.data, 4, txt.ctypes.data, 3, C.byref(n_out)) == -1        # output buffer too small
     assert L.sab200_unpack(txt.ctypes.data, 8, buf.ctypes.data, 16, C.byref(n_out)) == -1     # truncated header

@@ -156,6 +156,8 @@ def test_c3_repetitive_256mib(gpu_lib, oracle):
     s = gen.repetitive(256 << 20)
     sa = SuffixArray(s)
     assert SuffixArray.from_parts(s, sa.sa) is not None      # GPU linear-time check (a6 semantics)
+    assert oracle.sufcheck(s, sa.sa)                         # CPU linear-time verifier on the full array
+    assert np.array_equal(sa.sa, oracle.saca(s))             # bit-exact against the oracle's own construction
     pc.sampled_order_check(s, sa.sa)
     # stress variants (correctness only): pure periodic and all-equal
     for t in (gen.repetitive(8 << 20, block=1 << 12, mut_rate=0.0), np.full(4 << 20, ord("a"), dtype=np.uint8)):
@@ -163,12 +165,16 @@ def test_c3_repetitive_256mib(gpu_lib, oracle):
 
 
 def test_c2_dna_1gib(gpu_lib, oracle):
-    # BASELINE.json configs[1] at full size: GPU verifier + checksum + sampled neighbour order on CPU,
-    # and a bit-exact diff of a 64 MiB prefix-text run against the oracle's verifier
+    # BASELINE.json configs[1] at full size: the oracle's linear-time verifier over the whole array (the suffix
+    # array of a text is unique, so "valid" is "bit-exact"), the GPU verifier, and a bit-exact diff of a
+    # 256 MiB prefix-text construction against the oracle's own construction
     s = gen.dna_like(1 << 30)
     sa = SuffixArray(s)
     assert SuffixArray.from_parts(s, sa.sa) is not None
+    assert oracle.sufcheck(s, sa.sa)
     pc.sampled_order_check(s, sa.sa)
+    head = np.ascontiguousarray(s[:256 << 20])
+    assert np.array_equal(SuffixArray(head).sa, oracle.saca(head))
     # search on the finished 1 GiB index (C5 shape, reduced pattern count): exact (lo, hi) / bool
     sa.enable_buckets()
     pats, offs = gen.patterns(s, 20000)
