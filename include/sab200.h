@@ -67,8 +67,12 @@ typedef struct sab200_stats {
  * (src/sa.rs:25,32): fills all n+1 entries of `sa`, sa[0] = n (src/saca.rs:13), sa[1..] = the
  * suffix starts in increasing suffix order (what cdivsufsort::sort_in_place wrote, src/saca.rs:14).
  * `s` (n bytes) and `sa` (n+1 entries) are HOST buffers owned by the caller (src/sa.rs:24).
- * ngpus must be 1: multi-GPU construction runs one process per GPU through sab200_dist.h (driver:
- * suffix_array_b200/dist.py); other values return SAB200_ERR_ARGS.
+ * ngpus = 1: one GPU.  ngpus = 2..16 (at most sab200_device_count()): the text is block-sharded over the
+ * first ngpus devices of this process -- one host thread and one stream per GPU, an NCCL communicator
+ * created inside the library (ncclCommInitAll, cached between calls) -- and built by the distributed
+ * sample sort + prefix doubling described under "multi-GPU" below; every GPU uploads its own shard and
+ * downloads its own slice of the suffix array over its own PCIe link.  Returns SAB200_ERR_NCCL when NCCL
+ * is not installed or a collective fails.  ngpus = 0 means "all visible devices".
  * The reference panics when n > MAX_LENGTH (src/saca.rs:10); this returns SAB200_ERR_ARGS. */
 int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus);
 
@@ -132,6 +136,68 @@ int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_t* d_pats, 
 uint64_t sab200_pack_bound(uint64_t sa_len);
 int32_t sab200_pack(const uint32_t* sa, uint64_t sa_len, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
 int32_t sab200_unpack(const uint8_t* bytes, uint64_t nbytes, uint32_t* sa, uint64_t sa_cap, uint64_t* sa_len);
+
+/* ---- multi-GPU construction, one rank per GPU ------------------------------------------------
+ * The sharded form of the same saca() (src/saca.rs:9-15) for callers that already run one process (or
+ * thread) per GPU: rank g of P holds text positions [g*B, min((g+1)*B, n)), B = max(1, ceil(n / P)), followed
+ * by up to SAB200_SHARD_HALO bytes of the next shard, and receives a contiguous slice of the suffix array.
+ * The exchange steps (key all-to-all of the sample sort, rank requests / answers / updates of every doubling
+ * round) are NCCL collectives enqueued by the library on its own stream.
+ *
+ *   one process per GPU:  rank 0 calls sab200_comm_unique_id, the host language broadcasts the 128 bytes,
+ *                         every rank calls sab200_comm_create_nccl(id, rank, nranks, device).
+ *   custom transport:     sab200_comm_create_callbacks -- the caller supplies the three collectives (the
+ *                         CPU tests run the whole driver over gloo this way).  Buffers handed to a callback
+ *                         are device pointers of the rank's GPU; the library stream is idle during the call.
+ */
+#define SAB200_SHARD_HALO 64u
+#define SAB200_MAX_RANKS 16
+typedef struct sab200_comm sab200_comm;
+typedef struct sab200_comm_callbacks {
+    void* user;
+    /* recv[r*bytes .. (r+1)*bytes) = rank r's send[0 .. bytes) */
+    int32_t (*all_gather)(void* user, const void* send, void* recv, uint64_t bytes);
+    /* in-place sum of count u64 values over all ranks */
+    int32_t (*all_reduce_sum_u64)(void* user, uint64_t* buf, uint64_t count);
+    /* send[send_off[d] .. +send_bytes[d]) goes to rank d; recv[recv_off[s] .. +recv_bytes[s]) comes from rank s */
+    int32_t (*all_to_all_v)(void* user, const void* send, const uint64_t* send_bytes, const uint64_t* send_off,
+                            void* recv, const uint64_t* recv_bytes, const uint64_t* recv_off);
+} sab200_comm_callbacks;
+
+int32_t sab200_comm_unique_id(uint8_t id[128]);
+sab200_comm* sab200_comm_create_nccl(const uint8_t id[128], int32_t rank, int32_t nranks, int32_t device);
+sab200_comm* sab200_comm_create_callbacks(const sab200_comm_callbacks* cb, int32_t rank, int32_t nranks, int32_t device);
+void sab200_comm_destroy(sab200_comm* comm);
+
+/* Collective: every rank of `comm` calls it with its own shard of the same text of n bytes.
+ *   shard / shard_len   this rank's positions + halo: at least min(count + 64, n - lo) bytes (count = own positions);
+ *                       device memory of the rank's GPU when shard_on_device != 0, else host memory
+ *   out / out_cap       receives the slice (u32 suffix starts); may be NULL.  Device or host like the shard.
+ *   slice_len, sa_off   the slice holds suffix-array positions [sa_off, sa_off + slice_len); the sentinel
+ *                       sa[0] = n (src/saca.rs:13) is implied: rank 0's slice starts at position 1
+ *   d_slice             if not NULL: the slice inside the library's device arena (valid until the next call)
+ * Returns SAB200_ERR_ARGS when out_cap < slice_len (slice_len is still reported). */
+int32_t sab200_saca_sharded(sab200_comm* comm, const uint8_t* shard, uint64_t shard_len, uint64_t n, int32_t shard_on_device,
+                            uint32_t* out, uint64_t out_cap, int32_t out_on_device, uint64_t* slice_len, uint64_t* sa_off,
+                            const uint32_t** d_slice);
+
+#define SAB200_PHASES 16
+/* phase_ms index: 0 alphabet, 1 pack + splitters, 2 partition by destination, 3 key exchange, 4 local sort,
+ * 5 ranks + SA skeleton, 6 ranks to owners, 7 rebalance, 8 round requests/answers, 9 lazy look-ups,
+ * 10 round sorts, 11 re-rank, 12 rank updates, 13 new SA entries to their slices, 14 H2D, 15 D2H */
+typedef struct sab200_dist_stats {
+    uint32_t nranks, rank, rounds, lazy_isa, rank_layout /* 0 block, 1 block-cyclic */, rebalanced;
+    uint64_t slice_len, sa_off, all_to_all_bytes, collectives, resolved_empty;
+    uint64_t active[SAB200_MAX_ROUNDS]; /* active suffixes over all ranks entering round r (0 = after the initial sort) */
+    double phase_ms[SAB200_PHASES];     /* CUDA events on the rank's stream */
+    double total_ms;
+} sab200_dist_stats;
+/* Copies `bytes` from the library's device arena on `device` (a d_slice pointer) into host memory. */
+int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device);
+/* counters of the last sharded construction on `comm` */
+int32_t sab200_comm_stats(sab200_comm* comm, sab200_dist_stats* out);
+/* counters of rank `rank` of the last sab200_saca(..., ngpus > 1) of this process */
+int32_t sab200_multi_stats(int32_t rank, sab200_dist_stats* out);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 int32_t sab200_get_stats(sab200_stats* out);

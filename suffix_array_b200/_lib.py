@@ -57,6 +57,30 @@ class Stats(C.Structure):
         return d
 
 
+PHASES = 16
+
+
+class DistStats(C.Structure):
+    """include/sab200.h sab200_dist_stats"""
+    _fields_ = [
+        ("nranks", C.c_uint32), ("rank", C.c_uint32), ("rounds", C.c_uint32), ("lazy_isa", C.c_uint32),
+        ("rank_layout", C.c_uint32), ("rebalanced", C.c_uint32),
+        ("slice_len", C.c_uint64), ("sa_off", C.c_uint64), ("all_to_all_bytes", C.c_uint64), ("collectives", C.c_uint64),
+        ("resolved_empty", C.c_uint64),
+        ("active", C.c_uint64 * MAX_ROUNDS),
+        ("phase_ms", C.c_double * PHASES),
+        ("total_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        d["active"] = d["active"][:d["rounds"] + 1]
+        return d
+
+
 def build(verbose=False):
     """Compiles the CUDA engine in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
     import subprocess
@@ -108,6 +132,14 @@ def _bind(L):
         "sab200_pack_bound": ([u64], u64),
         "sab200_pack": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
         "sab200_unpack": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
+        "sab200_comm_unique_id": ([vp], i32),
+        "sab200_comm_create_nccl": ([C.c_char_p, i32, i32, i32], vp),
+        "sab200_comm_create_callbacks": ([vp, i32, i32, i32], vp),
+        "sab200_comm_destroy": ([vp], None),
+        "sab200_saca_sharded": ([vp, vp, u64, u64, i32, vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp)], i32),
+        "sab200_copy_from_device": ([vp, vp, u64, i32], i32),
+        "sab200_comm_stats": ([vp, C.POINTER(DistStats)], i32),
+        "sab200_multi_stats": ([i32, C.POINTER(DistStats)], i32),
     }
     for name, (args, res) in _opt.items():
         f = getattr(L, name)

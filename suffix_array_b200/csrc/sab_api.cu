@@ -156,7 +156,7 @@ int sab_ensure_scan(SabContext* c, size_t tiles) {
 }
 
 // ------------------------------------------------------------------ per-launch event timing
-static cudaEvent_t sab_event_get(SabContext* c) {
+cudaEvent_t sab_event_get(SabContext* c) {
     if (!c->event_pool.empty()) {
         cudaEvent_t e = c->event_pool.back();
         c->event_pool.pop_back();
@@ -228,6 +228,9 @@ static int run_device(SabContext* c, const u8* d_s, u64 n, u32* d_sa) {
     return rc;
 }
 
+static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P);  // sab_dist.cuh
+static void sab_multi_shutdown();
+
 // ------------------------------------------------------------------ extern "C"
 extern "C" {
 
@@ -246,10 +249,17 @@ int32_t sab200_saca_device(const uint8_t* d_s, uint64_t n, uint32_t* d_sa, int32
 }
 
 int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
-    if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH || ngpus != 1) {
+    if (ngpus == 0) ngpus = sab200_device_count() > SAB_MAX_RANKS ? SAB_MAX_RANKS : sab200_device_count();
+    if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH || ngpus < 0 || ngpus > SAB_MAX_RANKS) {
         sab_set_error("sab200_saca: bad arguments (n=%llu, ngpus=%d)", (unsigned long long)n, (int)ngpus);
         return SAB_ERR_ARGS;
     }
+    if (ngpus < 1 || ngpus > sab200_device_count()) {
+        sab_set_error("sab200_saca: %d GPUs requested, %d visible; libsab200 has no CPU fallback", (int)ngpus,
+                      (int)sab200_device_count());
+        return ngpus < 1 ? SAB_ERR_CUDA : SAB_ERR_ARGS;
+    }
+    if (ngpus > 1) return sab_saca_multi(s, n, sa, ngpus);
     SabContext* c = sab_get_context(0);
     if (!c) return SAB_ERR_CUDA;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -690,6 +700,7 @@ const char* sab200_version(void) {
 }
 
 void sab200_shutdown(void) {
+    sab_multi_shutdown();
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     for (int d = 0; d < SAB_MAX_DEVICES; ++d) {
         if (g_ctx[d]) {

@@ -12,6 +12,7 @@
 #pragma once
 #include "../../include/sab200.h"
 #include "sab_context.cuh"
+#include "sab_radix.cuh"
 
 #ifndef SAB_EMU
 #include <dlfcn.h>
@@ -30,6 +31,7 @@ struct sab200_comm {
     // accounting of the last construction
     u64 bytes_sent = 0;
     u32 collectives = 0;
+    sab200_dist_stats last;
 };
 #define SAB_COMM_SCRATCH ((size_t)1 << 20)
 
@@ -229,9 +231,10 @@ struct A2APlan {
     u64 scount[SAB_MAX_RANKS], rcount[SAB_MAX_RANKS];
     u64 stotal, rtotal;
 };
-static int sab_comm_plan(sab200_comm* cm, cudaStream_t st, const u64* send_counts, A2APlan* pl) {
+static int sab_comm_plan(sab200_comm* cm, cudaStream_t st, const u64* send_counts, A2APlan* pl, u64* mat_out) {
     const int P = cm->P;
-    u64 mat[SAB_MAX_RANKS * SAB_MAX_RANKS];
+    u64 mat_[SAB_MAX_RANKS * SAB_MAX_RANKS];
+    u64* mat = mat_out ? mat_out : mat_;
     SAB_TRY(sab_comm_count_matrix(cm, st, send_counts, mat));
     pl->stotal = pl->rtotal = 0;
     for (int d = 0; d < P; ++d) {

@@ -91,6 +91,7 @@ static inline T* sab_arena_take(SabContext* c, size_t count) {
     return (T*)(c->arena + off);
 }
 
+cudaEvent_t sab_event_get(SabContext* c);
 void sab_prof_begin(SabContext* c, int kind);
 void sab_prof_end(SabContext* c);
 void sab_prof_collect(SabContext* c);

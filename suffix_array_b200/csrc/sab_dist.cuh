@@ -1,10 +1,32 @@
-// sab_dist.cuh -- per-rank step functions of the multi-GPU construction (include/sab200_dist.h).
-// The kernels are the single-GPU ones (onesweep with a destination-rank digit, init_ranks / rerank with
-// their list outputs); the collectives between the steps belong to the host driver.
+// sab_dist.cuh -- multi-GPU suffix-array construction: one rank per GPU, distributed sample sort of the packed
+// keys followed by prefix doubling with a fixed number of exchange steps per round (include/sab200.h,
+// "multi-GPU").  The reference has nothing distributed; this is the sharded form of the same
+// saca() (/root/reference/src/saca.rs:9-15).
+//
+//   rank g of P owns text positions [g*B, (g+1)*B) and the rank[] entries the RankLayout gives it
+//   1  byte histogram                       all_reduce   -> common code table / key shape (sab_plan_alphabet)
+//   2  keys of own positions; splitters     all_gather   of 2048 sampled keys per rank
+//   3  partition by destination (onesweep pass, digit = #splitters <= key)         all_to_all (key, i)
+//   4  local radix sort -> a contiguous slice of the suffix array; equal keys share a destination, so groups
+//      never straddle GPUs and all re-ranking is local
+//   5  init_ranks: slice of sa[], active list (r1, i), bucket directory over the slice's sorted keys
+//   6  inverse suffix array at the owners: LAZY when at most a quarter of the suffixes is active (only their
+//      ranks travel; a request that finds EMPTY is a suffix that was unique after step 4: the owner packs its
+//      key from its text shard, the key travels to the slice that holds it and its rank comes back), else all
+//      ranks travel and rank[] is dealt block-cyclically (any region of the text is spread over all owners)
+//   7  rounds h = k, 2k, ...:  requests i+h -> owners, answers back                2 x all_to_all (+2 lazy)
+//      the list keeps its order (answers are placed by list position), so the in-group sort of the
+//      single-GPU path applies; re-rank; changed ranks -> owners                     all_to_all
+//
+// Every step is enqueued on the rank's library stream; the host only waits where it needs a count.
 #pragma once
-#include "../../include/sab200_dist.h"
+#include <algorithm>
+#include <thread>
+
+#include "sab_comm.cuh"
 #include "sab_saca.cuh"
 
+// ------------------------------------------------------------------ kernels
 template <typename KeyT, typename DigitOp>
 __global__ void __launch_bounds__(256) digit_count_kernel(const KeyT* __restrict__ keys, u64 n, DigitOp dop, u64* __restrict__ counts) {
     SAB_SHARED_ARRAY(u32, s_c, 256);
@@ -17,11 +39,17 @@ __global__ void __launch_bounds__(256) digit_count_kernel(const KeyT* __restrict
     if (c) atomicAdd((unsigned long long*)&counts[threadIdx.x], (unsigned long long)c);
 }
 
-__global__ void iota_base_kernel(u32* __restrict__ out, u64 n, u32 base) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = base + (u32)i;
-}
 __global__ void hist_widen_kernel(const u32* __restrict__ h32, u64* __restrict__ h64) { h64[threadIdx.x] = h32[threadIdx.x]; }
+
+// out[j] = keys[j * step] for the first min(S, ceil(count / step)) samples; out[S] = how many
+__global__ void sample_keys_kernel(const u64* __restrict__ keys, u64 count, u64 step, u32 S, u64* __restrict__ out) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 have = count ? (count + step - 1) / step : 0;
+    const u32 ns = have < S ? (u32)have : S;
+    if (j < ns) out[j] = keys[(u64)j * step];
+    if (j == 0) out[S] = ns;
+}
+
 // local slot of position q on its owner: q - lo under the block layout (lay.cyc = 0), lay.slot() otherwise
 __global__ void dist_scatter_kernel(const u32* __restrict__ pos, const u32* __restrict__ val, u64 n, u32 lo, RankLayout lay,
                                     u32* __restrict__ rank_local) {
@@ -36,11 +64,47 @@ __global__ void dist_gather_kernel(const u32* __restrict__ pos, u64 n, u32 add, 
         out[i] = rank_local[lay.cyc ? lay.slot(q, 0) : q - lo];
     }
 }
-__global__ void dist_make_keys_kernel(const u32* __restrict__ r1, const u32* __restrict__ r2, u64 n, u64* __restrict__ key64) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) key64[i] = ((u64)r1[i] << 32) | r2[i];
+// The requests left in owner order; the answers come back in the same order and return to the LIST position
+// of their record: key64[pos[t]] = (r1[pos[t]] << 32) | r2[t].  The list stays grouped by r1.
+__global__ void dist_place_keys_kernel(const u32* __restrict__ r1, const u32* __restrict__ pos, const u32* __restrict__ r2, u64 m,
+                                       u64* __restrict__ key64) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) {
+        const u32 p = pos[t];
+        key64[p] = ((u64)r1[p] << 32) | r2[t];
+    }
 }
 
+// ---- lazy inverse suffix array, distributed (see the file header, step 6)
+__global__ void __launch_bounds__(256)
+dist_lazy_collect_kernel(const u32* __restrict__ q, const u32* __restrict__ ans, u64 count, u32 h, u64 shard_lo,
+                         const u8* __restrict__ text, u64 n_rel, const u16* __restrict__ lut, u32 base, int k,
+                         u64* __restrict__ keys_out, u32* __restrict__ slot_out, u32* __restrict__ counter) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count || ans[t] != SAB_RANK_EMPTY) return;
+    const u32 p = atomicAdd(counter, 1u);
+    keys_out[p] = pack_key_at(text, n_rel, lut, base, k, (u64)q[t] + h - shard_lo);
+    slot_out[p] = (u32)t;
+}
+// rank of a suffix that was unique after the initial sort = SA position of its key in this slice
+__global__ void __launch_bounds__(256)
+dist_lookup_kernel(const u64* __restrict__ sorted, u64 R, const u32* __restrict__ dir, int dir_shift, const u64* __restrict__ keys,
+                   u64 count, u32 sa_off, u32* __restrict__ rank_out) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    rank_out[t] = sa_off + (u32)sorted_key_position(sorted, R, dir, dir_shift, keys[t]);
+}
+__global__ void __launch_bounds__(256)
+dist_lazy_fill_kernel(const u32* __restrict__ slot, const u32* __restrict__ rank, u64 count, const u32* __restrict__ q, u32 h,
+                      u32 lo, u32* __restrict__ ans, u32* __restrict__ rank_local) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const u32 s = slot[t], r = rank[t];
+    ans[s] = r;
+    rank_local[(u64)q[s] + h - lo] = r;  // memoised: the next request for this position is answered directly
+}
+
+// ------------------------------------------------------------------ host helpers
 static inline unsigned sab_grid(SabContext* c, u64 n, u64 per_block, int waves) {
     u64 g = div_up64(n, per_block);
     const u64 gmax = (u64)c->sm_count * (u64)waves;
@@ -48,7 +112,7 @@ static inline unsigned sab_grid(SabContext* c, u64 n, u64 per_block, int waves) 
     return (unsigned)(g ? g : 1);
 }
 
-// counts of the first `bins` digits -> host; exclusive prefix -> c->d_gbase[0..256)
+// counts of the first `bins` digits -> host; exclusive prefix over all 256 bins -> c->d_gbase[0..256)
 template <typename KeyT, typename DigitOp>
 static int sab_count_and_base(SabContext* c, const KeyT* d_keys, u64 count, DigitOp dop, int bins, u64* counts_host) {
     cudaStream_t st = c->stream;
@@ -57,6 +121,7 @@ static int sab_count_and_base(SabContext* c, const KeyT* d_keys, u64 count, Digi
     if (count) {
         SAB_LAUNCH((digit_count_kernel<KeyT, DigitOp>), sab_grid(c, count, 256 * 16, 8), 256, 0, st, d_keys, count, dop, d_cnt);
         SAB_LAUNCH_CHECK();
+        c->stats.kernel_launches++;
     }
     u64* h = (u64*)(c->h_small + 1024);  // 512 x u64 of the pinned scratch
     SAB_CUDA_TRY(cudaMemcpyAsync(h, d_cnt, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -72,470 +137,825 @@ static int sab_count_and_base(SabContext* c, const KeyT* d_keys, u64 count, Digi
     return SAB_OK;
 }
 
-static SabContext* sab_dist_ctx(int device) {
-    SabContext* c = sab_get_context(device);
-    if (c) cudaSetDevice(c->device);
-    return c;
+// host mirror of RankLayout::owner / slot (sab_radix.cuh)
+static inline u32 sab_layout_owner_host(const RankLayout& L, u64 q) {
+    if (L.cyc) return (u32)((q >> L.shift) % (L.pmax + 1u));
+    const u32 o = (u32)(q / L.B);
+    return o < L.pmax ? o : L.pmax;
+}
+static inline u64 sab_layout_slot_host(const RankLayout& L, u64 q, u32 o) {
+    if (L.cyc) return (((q >> L.shift) / (L.pmax + 1u)) << L.shift) | (q & (u64)(L.B - 1u));
+    return q - (u64)o * L.B;
 }
 
-extern "C" int32_t sab200_dist_hist(const uint8_t* d_text, uint64_t len, uint64_t* d_hist, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    std::lock_guard<std::mutex> lk(c->mu);
+// Two-ended bump allocator over the context arena: long-lived arrays grow from the bottom, the temporaries of
+// a phase / round from the top (released by restoring `hi`).
+struct DistArena {
+    char* base;
+    size_t lo, hi;
+    bool ok;
+    template <typename T>
+    T* bot(size_t count) {
+        const size_t o = sab_align_up(lo, 256), e = o + count * sizeof(T);
+        if (e > hi) {
+            ok = false;
+            return nullptr;
+        }
+        lo = e;
+        return (T*)(base + o);
+    }
+    template <typename T>
+    T* top(size_t count) {
+        const size_t bytes = sab_align_up(count * sizeof(T), 256);
+        if (hi < lo + bytes) {
+            ok = false;
+            return nullptr;
+        }
+        hi -= bytes;
+        return (T*)(base + hi);
+    }
+};
+#define SAB_ARENA_CHECK(A)                                                                                     \
+    do {                                                                                                       \
+        if (!(A).ok) {                                                                                         \
+            sab_set_error("%s:%d: device arena exhausted (%zu bytes)", __FILE__, __LINE__, c->arena_bytes);    \
+            return SAB_ERR_OOM;                                                                                \
+        }                                                                                                      \
+    } while (0)
+
+// phase timer: CUDA events at the phase boundaries of the rank's stream, read once at the end
+struct DistPhases {
+    SabContext* c;
+    std::vector<std::pair<int, cudaEvent_t> > ev;
+    void mark(int phase) {
+        cudaEvent_t e = sab_event_get(c);
+        cudaEventRecord(e, c->stream);
+        ev.push_back(std::make_pair(phase, e));
+    }
+    void collect(double* phase_ms, double* total_ms) {  // the stream must be idle
+        for (size_t i = 0; i + 1 < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i].second, ev[i + 1].second);
+            if (ev[i].first >= 0 && ev[i].first < SAB200_PHASES) phase_ms[ev[i].first] += ms;
+        }
+        if (ev.size() >= 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev.front().second, ev.back().second);
+            *total_ms = ms;
+        }
+        for (auto& p : ev) c->event_pool.push_back(p.second);
+        ev.clear();
+    }
+};
+
+struct DistResult {
+    u32* d_slice;
+    u64 slice_len, sa_off;
+};
+
+static inline int sab_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Arena for a rank that owns B text positions: sized for slices up to ~1.3 B records with all suffixes active,
+// capped by the free device memory (a grow-only arena: no cudaMalloc in steady state).
+static int sab_dist_reserve(SabContext* c, u64 B) {
+    const size_t recs = (size_t)(B + B / 3) + ((size_t)1 << 20);
+    size_t want = recs * 72 + ((size_t)256 << 20);
+    size_t free_b = 0, total_b = 0;
+    SAB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = (size_t)((double)(free_b + c->arena_bytes) * 0.94);
+    if (want > avail) want = avail;
+    return sab_arena_reserve(c, want);
+}
+
+struct DistRun {
+    sab200_comm* cm;
+    SabContext* c;
+    DistArena A;
+    DistPhases ph;
+    RankLayout lay;
+    u32* rank_local;
+    u64 lo;  // first text position of this rank
+
+    // rank[idx[t]] = val[t] on the GPU that owns text position idx[t]; records with idx = 0xFFFFFFFF are dropped
+    int send_ranks(const u32* idx, const u32* val, u64 cnt) {
+        cudaStream_t st = c->stream;
+        const size_t mark = A.hi;
+        u32* kp = A.top<u32>(cnt + 8);
+        u32* vp = A.top<u32>(cnt + 8);
+        SAB_ARENA_CHECK(A);
+        OwnerDigit dop;
+        dop.add = 0;
+        dop.lay = lay;
+        u64 counts[SAB_MAX_RANKS];
+        SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, idx, cnt, dop, cm->P, counts)));
+        A2APlan pl;
+        SAB_TRY(sab_comm_plan(cm, st, counts, &pl, nullptr));
+        if (cnt) {
+            SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(cnt, PassShape<u32>::THREADS * PassShape<u32>::ITEMS)));
+            SAB_TRY((sab_launch_pass_op<u32, false, OwnerDigit>(c, idx, kp, val, vp, cnt, dop, c->d_gbase)));
+        }
+        u32* ri = A.top<u32>(pl.rtotal + 8);
+        u32* rr = A.top<u32>(pl.rtotal + 8);
+        SAB_ARENA_CHECK(A);
+        SAB_TRY(sab_comm_exchange(cm, st, pl, kp, ri, sizeof(u32)));
+        SAB_TRY(sab_comm_exchange(cm, st, pl, vp, rr, sizeof(u32)));
+        if (pl.rtotal) {
+            SAB_LAUNCH(dist_scatter_kernel, (unsigned)div_up64(pl.rtotal, 256), 256, 0, st, (const u32*)ri, (const u32*)rr, pl.rtotal,
+                       (u32)lo, lay, rank_local);
+            SAB_LAUNCH_CHECK();
+            c->stats.kernel_launches++;
+        }
+        A.hi = mark;
+        return SAB_OK;
+    }
+};
+
+// d_text: this rank's shard + halo on the device (text_len bytes).  The arena `A0` starts behind whatever the
+// caller placed at its bottom.  Enqueues on c->stream; the stream is idle when the function returns.
+static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8* d_text, u64 text_len, u64 n, DistResult* res,
+                         sab200_dist_stats* ds) {
+    const int P = cm->P, g = cm->rank;
     cudaStream_t st = c->stream;
+    SabStats& S = c->stats;
+    S.n = n;
+    cm->bytes_sent = 0;
+    cm->collectives = 0;
+    const u64 B = n ? div_up64(n, (u64)P) : 1;
+    const u64 lo = (u64)g * B < n ? (u64)g * B : n;
+    const u64 hi = lo + B < n ? lo + B : n;
+    const u64 count = hi - lo;
+    res->d_slice = nullptr;
+    res->slice_len = 0;
+    res->sa_off = 1;
+    ds->nranks = (u32)P;
+    ds->rank = (u32)g;
+    if (n == 0) return SAB_OK;  // the suffix array is the sentinel alone
+    const u64 avail = (n - lo) < count + SAB200_SHARD_HALO ? (n - lo) : count + SAB200_SHARD_HALO;
+    if (text_len < avail) {
+        sab_set_error("rank %d: shard of %llu bytes, need %llu (own positions + halo)", g, (unsigned long long)text_len,
+                      (unsigned long long)avail);
+        return SAB_ERR_ARGS;
+    }
+    DistRun R_;
+    R_.cm = cm;
+    R_.c = c;
+    R_.A = A0;
+    R_.ph.c = c;
+    R_.lo = lo;
+    R_.rank_local = nullptr;
+    DistArena& A = R_.A;
+    DistPhases& ph = R_.ph;
+    SAB_TRY(sab_ensure_scan(c, (size_t)div_up64(count + count / 2 + 4096, SAB_GSORT_TILE)));
+
+    // ---- 1. common alphabet / key shape
+    ph.mark(0);
     u32* d_h32 = c->d_counters + 16;
     SAB_CUDA_TRY(cudaMemsetAsync(d_h32, 0, 256 * sizeof(u32), st));
-    if (len) {
-        SAB_LAUNCH(alphabet_hist_kernel, sab_grid(c, len, 256 * 64, 8), 256, 0, st, d_text, len, d_h32);
+    if (count) {
+        SAB_LAUNCH(alphabet_hist_kernel, sab_grid(c, count, 256 * 64, 8), 256, 0, st, d_text, count, d_h32);
         SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
     }
-    SAB_LAUNCH(hist_widen_kernel, 1, 256, 0, st, (const u32*)d_h32, d_hist);
+    SAB_LAUNCH(hist_widen_kernel, 1, 256, 0, st, (const u32*)d_h32, c->d_ghist);
     SAB_LAUNCH_CHECK();
+    SAB_TRY(sab_comm_all_reduce_u64(cm, st, c->d_ghist, 256));
+    u64* h64 = (u64*)(c->h_small + 1024);
+    SAB_CUDA_TRY(cudaMemcpyAsync(h64, c->d_ghist, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_plan(const uint64_t* hist256, uint64_t n, uint16_t* lut256, int32_t* b, int32_t* k) {
-    if (!hist256 || !lut256 || !b || !k) return SAB_ERR_ARGS;
+    u16 lut[256];
     u32 sigma = 0, base = 2;
-    int kk = 1, bits = 1;
-    sab_plan_alphabet(hist256, n, lut256, &sigma, &base, &kk, &bits);
-    *b = (int32_t)base;
-    *k = kk;
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_pack(const uint8_t* d_text, uint64_t shard_lo, uint64_t count, uint64_t n,
-                                    const uint16_t* lut256, int32_t b, int32_t k, uint64_t* d_keys, uint32_t* d_idx,
-                                    int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (shard_lo > n || b < 2 || k < 1 || k > 64) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    cudaStream_t st = c->stream;
-    if (count == 0) return SAB_OK;
-    u16* d_lut = (u16*)(c->d_counters + 16 + 256);
-    memcpy(c->h_small + 384, lut256, 256 * sizeof(u16));
-    SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, 256 * sizeof(u16), cudaMemcpyHostToDevice, st));
-    // the shard buffer holds count + 64 bytes (halo) at most: never read past them (k <= 64 symbols per key)
-    const u64 avail = (n - shard_lo) < count + 64 ? (n - shard_lo) : count + 64;
-    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, avail, count,
-               (const u16*)d_lut, (u32)b, (int)k, sab_pow_u64((u64)b, k - 1), d_keys);
-    SAB_LAUNCH_CHECK();
-    SAB_LAUNCH(iota_base_kernel, (unsigned)div_up64(count, 256), 256, 0, st, d_idx, count, (u32)shard_lo);
-    SAB_LAUNCH_CHECK();
-    SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_partition_keys(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count,
-                                              const uint64_t* splitters, int32_t nsplit, uint64_t* d_keys_out,
-                                              uint32_t* d_idx_out, uint64_t* counts, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (nsplit < 0 || nsplit > SAB_MAX_RANKS - 1 || !counts) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    SplitterDigit dop;
-    dop.np = nsplit;
-    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) dop.s[i] = i < nsplit ? splitters[i] : ~0ull;
-    SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, d_keys, count, dop, nsplit + 1, counts)));
-    if (count) {
-        constexpr int TILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
-        SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
-        SAB_TRY((sab_launch_pass_op<u64, false, SplitterDigit>(c, d_keys, d_keys_out, d_idx, d_idx_out, count, dop, c->d_gbase)));
+    int k = 1, key_bits = 1;
+    {
+        u64 hh[256];
+        memcpy(hh, h64, sizeof(hh));
+        sab_plan_alphabet(hh, n, lut, &sigma, &base, &k, &key_bits);
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
+    S.sigma = sigma;
+    S.bits_per_symbol = (u32)sab_ceil_log2_u64(base);
+    S.symbols_per_key = (u32)k;
+    u16* d_lut = (u16*)(c->d_counters + 16 + 256);
+    memcpy(c->h_small + 384, lut, sizeof(lut));
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
 
-extern "C" int32_t sab200_dist_sort_pairs(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
-                                          int32_t key_bits, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (key_bits < 0 || key_bits > 64) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
+    // ---- 2. keys of own positions, splitters from a sample
+    ph.mark(1);
+    u64* keysA = A.top<u64>(count + 8);
+    SAB_ARENA_CHECK(A);
+    if (count) {
+        sab_prof_begin(c, 2);
+        SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, avail, count,
+                   (const u16*)d_lut, base, k, sab_pow_u64(base, k - 1), keysA);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
+    }
+    u64 splitters[SAB_MAX_RANKS];
+    for (int i = 0; i < SAB_MAX_RANKS; ++i) splitters[i] = ~0ull;
+    if (P > 1) {
+        const u32 NS = 2048;
+        const u64 step = count / NS ? count / NS : 1;
+        u64* d_sample = cm->d_small;
+        SAB_LAUNCH(sample_keys_kernel, (NS + 255) / 256, 256, 0, st, (const u64*)keysA, count, step, NS, d_sample);
+        SAB_LAUNCH_CHECK();
+        SAB_TRY(sab_comm_all_gather(cm, st, d_sample, d_sample + (NS + 1), (NS + 1) * sizeof(u64)));
+        SAB_CUDA_TRY(cudaMemcpyAsync(cm->h_small, d_sample + (NS + 1), (size_t)P * (NS + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        SAB_CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<u64> pool;
+        pool.reserve((size_t)P * NS);
+        for (int r = 0; r < P; ++r) {
+            const u64* row = cm->h_small + (size_t)r * (NS + 1);
+            const u64 have = row[NS] <= NS ? row[NS] : NS;
+            pool.insert(pool.end(), row, row + have);
+        }
+        std::sort(pool.begin(), pool.end());
+        for (int i = 0; i + 1 < P; ++i) {
+            size_t at = (size_t)(i + 1) * pool.size() / (size_t)P;
+            if (at >= pool.size()) at = pool.size() - 1;
+            splitters[i] = pool.empty() ? 0 : pool[at];
+        }
+    }
+
+    // ---- 3. partition by destination (digit = number of splitters <= key), payload = global position
+    ph.mark(2);
+    SplitterDigit sdop;
+    sdop.np = P - 1;
+    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) sdop.s[i] = i < P - 1 ? splitters[i] : ~0ull;
+    u64 cnt_dst[SAB_MAX_RANKS];
+    SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, keysA, count, sdop, P, cnt_dst)));
+    A2APlan pk;
+    u64 mat[SAB_MAX_RANKS * SAB_MAX_RANKS];
+    SAB_TRY(sab_comm_plan(cm, st, cnt_dst, &pk, mat));
+    const u64 R = pk.rtotal;
+    u64 sa_off = 1;
+    for (int r = 0; r < g; ++r)
+        for (int s = 0; s < P; ++s) sa_off += mat[(size_t)s * P + r];
+    u64* partK = A.top<u64>(count + 8);
+    u32* partI = A.top<u32>(count + 8);
+    SAB_ARENA_CHECK(A);
+    constexpr int PTILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
+    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64((count > R ? count : R) + 1, PTILE)));
+    SAB_TRY(sab_ensure_scan(c, (size_t)div_up64(R + 4096, SAB_GSORT_TILE)));
+    if (count)
+        SAB_TRY((sab_launch_pass_op<u64, true, SplitterDigit>(c, keysA, partK, nullptr, partI, count, sdop, c->d_gbase, nullptr, (u32)lo)));
+
+    // ---- 4. key exchange
+    ph.mark(3);
+    u64* K0 = A.bot<u64>(R + 8);
+    u32* V0 = A.bot<u32>(R + 8);
+    SAB_ARENA_CHECK(A);
+    SAB_TRY(sab_comm_exchange(cm, st, pk, partK, K0, sizeof(u64)));
+    SAB_TRY(sab_comm_exchange(cm, st, pk, partI, V0, sizeof(u32)));
+    A.hi = A0.hi;  // keysA, partK, partI are dead once the exchange has run (stream order)
+
+    // ---- 5. local sort: this rank's slice of the suffix array
+    ph.mark(4);
     SortBuffers<u64> buf;
-    buf.k[0] = d_k0;
-    buf.k[1] = d_k1;
-    buf.v[0] = d_v0;
-    buf.v[1] = d_v1;
+    buf.k[0] = K0;
+    buf.v[0] = V0;
+    buf.k[1] = A.bot<u64>(R + 8);
+    buf.v[1] = A.bot<u32>(R + 8);
     buf.cur = 0;
-    u32 passes = 0;
-    const int rc = sab_radix_sort<u64>(c, buf, count, 0, key_bits, false, &passes);
-    if (rc != SAB_OK) return rc;
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return buf.cur;
-}
+    u32* sa_local = A.bot<u32>(R + 8);
+    u32* r1buf = A.bot<u32>(R + 8);
+    SAB_ARENA_CHECK(A);
+    SAB_TRY(sab_radix_sort<u64>(c, buf, R, 0, key_bits, /*iota=*/false, &S.passes[0]));
 
-extern "C" int32_t sab200_dist_init_ranks(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count, uint32_t sa_off,
-                                          uint32_t* d_sa_local, uint32_t* d_rank_seq, uint32_t* d_act_r1,
-                                          uint32_t* d_act_idx, uint64_t* n_active, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (!n_active) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    *n_active = 0;
-    if (count == 0) return SAB_OK;
-    cudaStream_t st = c->stream;
-    const u64 tiles = div_up64(count, SAB_SCAN_TILE);
-    SAB_TRY(sab_ensure_scan(c, (size_t)tiles));
-    TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
+    // ---- 6. ranks, slice of sa[], active list, bucket directory over the slice's keys
+    ph.mark(5);
+    const u64* sortedK = buf.k[buf.cur];
+    const u32* sortedI = buf.v[buf.cur];
+    u64* freeK = buf.k[buf.cur ^ 1];
+    u32* act_idx = buf.v[buf.cur ^ 1];
+    u32* rank_seq = (u32*)freeK;
+    int dir_bits = sab_ceil_log2_u64(n) - 4;
+    if (dir_bits > 28) dir_bits = 28;
+    if (dir_bits > key_bits) dir_bits = key_bits;
+    if (dir_bits < 1) dir_bits = 1;
+    const int dir_shift = key_bits - dir_bits;
+    const u64 kmax = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+    const u64 klo = g > 0 ? splitters[g - 1] : 0ull;
+    u64 khi = g < P - 1 ? splitters[g] : kmax;
+    if (khi > kmax) khi = kmax;
+    if (khi < klo) khi = klo;
+    const u64 dlo = klo >> dir_shift;
+    const u64 dir_len = (khi >> dir_shift) - dlo + 2;
+    u32* dir = A.bot<u32>(dir_len + 8);
+    SAB_ARENA_CHECK(A);
+    u32* dir_shifted = dir - dlo;  // indexed by key >> dir_shift
     u32* d_m = c->d_counters;
-    SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, d_keys, d_idx, count, sa_off, (u32*)nullptr,
-               d_rank_seq, d_sa_local, d_act_r1, d_act_idx, d_m, (u32*)nullptr, 0, ts);
-    SAB_LAUNCH_CHECK();
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    u64 m = 0;
+    if (R) {
+        const u64 tiles = div_up64(R, SAB_SCAN_TILE);
+        TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
+        sab_prof_begin(c, 3);
+        SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, R, (u32)sa_off, (u32*)nullptr, rank_seq,
+                   sa_local, r1buf, act_idx, d_m, dir_shifted, dir_shift, ts);
+        sab_prof_end(c);
+        SAB_LAUNCH_CHECK();
+        S.kernel_launches++;
+        SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SAB_CUDA_TRY(cudaStreamSynchronize(st));
+        m = c->h_small[0];
+    }
+    // In lazy mode the round keys ping-pong inside ONE key buffer (the other keeps the sorted keys): the local
+    // list must fit its halves.
+    const u64 half = sab_align_up((size_t)(R + 8) / 2, 32);
+    u64 sums[2] = {m, (m > (R + 8) - half) ? 1ull : 0ull};
+    SAB_TRY(sab_comm_sum_u64(cm, st, sums, 2));
+    u64 tot = sums[0];
+    S.active[0] = m;
+    ds->active[0] = tot;
+    u32 round = 0;
+    bool lazy = false, rebalanced = false;
+    int layout_cyc = 0;
+    if (tot > 0) {
+        // ---- 7. inverse suffix array at the owners
+        ph.mark(6);
+        lazy = tot <= n / 4 && sums[1] == 0 && sab_env_int("SAB_DIST_LAZY", 1) != 0;
+        const char* lenv = getenv("SAB_RANK_LAYOUT");
+        layout_cyc = lazy ? 0 : 1;  // lazy look-ups pack keys from the owner's text shard: block ownership
+        if (!lazy && lenv && !strcmp(lenv, "block")) layout_cyc = 0;
+        u64 local_len;
+        if (layout_cyc) {
+            u64 per = n / (8ull * (u64)P);
+            int shift = 0;
+            while (shift < 20 && (2ull << shift) <= per) ++shift;
+            const u64 width = 1ull << shift;
+            const u64 blocks = div_up64(n + 1, width);
+            local_len = div_up64(blocks, (u64)P) << shift;
+            sab_rank_layout((u32)width, P, shift, &R_.lay);
+        } else {
+            local_len = B + 1;  // the last GPU also owns position n
+            sab_rank_layout((u32)B, P, -1, &R_.lay);
+        }
+        const RankLayout lay = R_.lay;
+        u32* rank_local = A.bot<u32>(local_len + 8);
+        SAB_ARENA_CHECK(A);
+        R_.rank_local = rank_local;
+        if (lazy) SAB_CUDA_TRY(cudaMemsetAsync(rank_local, 0xff, local_len * sizeof(u32), st));
+        {
+            const u32 on = sab_layout_owner_host(lay, n);  // the empty suffix has rank 0
+            if ((int)on == g) SAB_CUDA_TRY(cudaMemsetAsync(rank_local + sab_layout_slot_host(lay, n, on), 0, sizeof(u32), st));
+        }
+        if (lazy) SAB_TRY(R_.send_ranks(act_idx, r1buf, m));
+        else SAB_TRY(R_.send_ranks(sortedI, rank_seq, R));
+
+        // ---- 8. doubling rounds
+        SortBuffers<u64> rb;
+        u64 key_cap;
+        if (lazy) {
+            rb.k[0] = freeK;
+            rb.k[1] = freeK + half;
+            key_cap = (R + 8) - half;
+        } else {
+            rb.k[0] = freeK;
+            rb.k[1] = buf.k[buf.cur];
+            key_cap = R + 8;
+        }
+        rb.v[0] = act_idx;
+        rb.v[1] = buf.v[buf.cur];
+        rb.cur = 0;
+        const u64 val_cap = R + 8;
+        u32* sa_shifted = sa_local - (size_t)sa_off;  // ranks are global SA positions
+        const int rank_bits = sab_ceil_log2_u64(n + 2);
+        bool group_sort_on = SAB_GROUP_SORT != 0;
+        u64 h = (u64)k;
+        while (tot > 0) {
+            ++round;
+            if (round >= SAB_MAX_ROUNDS || h > n) {
+                sab_set_error("prefix doubling did not converge (round %u, h=%llu, active=%llu)", round, (unsigned long long)h,
+                              (unsigned long long)tot);
+                return SAB_ERR_INTERNAL;
+            }
+            const size_t topmark = A.hi;
+            // a. requests i + h to the owners (payload = list position), answers back in the same order
+            ph.mark(8);
+            u32* cur_idx = rb.v[rb.cur];
+            u32* ipart = A.top<u32>(m + 8);
+            u32* ppart = A.top<u32>(m + 8);
+            SAB_ARENA_CHECK(A);
+            OwnerDigit odop;
+            odop.add = (u32)h;
+            odop.lay = lay;
+            u64 cnt_own[SAB_MAX_RANKS];
+            SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, cur_idx, m, odop, P, cnt_own)));
+            A2APlan pr;
+            SAB_TRY(sab_comm_plan(cm, st, cnt_own, &pr, nullptr));
+            if (m) {
+                SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(m, PTILE)));
+                SAB_TRY((sab_launch_pass_op<u32, true, OwnerDigit>(c, cur_idx, ipart, nullptr, ppart, m, odop, c->d_gbase)));
+            }
+            const u64 nq = pr.rtotal;
+            u32* q = A.top<u32>(nq + 8);
+            u32* ans = A.top<u32>(nq + 8);
+            SAB_ARENA_CHECK(A);
+            SAB_TRY(sab_comm_exchange(cm, st, pr, ipart, q, sizeof(u32)));
+            if (nq) {
+                sab_prof_begin(c, 4);
+                SAB_LAUNCH(dist_gather_kernel, (unsigned)div_up64(nq, 256), 256, 0, st, (const u32*)q, nq, (u32)h, (u32)lo, lay,
+                           (const u32*)rank_local, ans);
+                sab_prof_end(c);
+                SAB_LAUNCH_CHECK();
+                S.kernel_launches++;
+            }
+            if (lazy) {
+                // b. requests that found EMPTY: key at the owner -> slice that holds the key -> rank back
+                ph.mark(9);
+                u64* keys_u = A.top<u64>(nq + 8);
+                u32* slot_u = A.top<u32>(nq + 8);
+                SAB_ARENA_CHECK(A);
+                u32* d_cnt = c->d_counters + 12;
+                SAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(u32), st));
+                if (nq) {
+                    SAB_LAUNCH(dist_lazy_collect_kernel, (unsigned)div_up64(nq, 256), 256, 0, st, (const u32*)q, (const u32*)ans, nq, (u32)h,
+                               lo, d_text, avail, (const u16*)d_lut, base, k, keys_u, slot_u, d_cnt);
+                    SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
+                }
+                SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 12, d_cnt, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                SAB_CUDA_TRY(cudaStreamSynchronize(st));
+                const u64 nu = c->h_small[12];
+                ds->resolved_empty += nu;
+                u64* kp = A.top<u64>(nu + 8);
+                u32* sp = A.top<u32>(nu + 8);
+                SAB_ARENA_CHECK(A);
+                u64 cnt_u[SAB_MAX_RANKS];
+                SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, keys_u, nu, sdop, P, cnt_u)));
+                A2APlan pu;
+                SAB_TRY(sab_comm_plan(cm, st, cnt_u, &pu, nullptr));
+                if (nu) {
+                    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(nu, PTILE)));
+                    SAB_TRY((sab_launch_pass_op<u64, false, SplitterDigit>(c, keys_u, kp, slot_u, sp, nu, sdop, c->d_gbase)));
+                }
+                u64* kq = A.top<u64>(pu.rtotal + 8);
+                u32* rk = A.top<u32>(pu.rtotal + 8);
+                u32* back = A.top<u32>(nu + 8);
+                SAB_ARENA_CHECK(A);
+                SAB_TRY(sab_comm_exchange(cm, st, pu, kp, kq, sizeof(u64)));
+                if (pu.rtotal) {
+                    SAB_LAUNCH(dist_lookup_kernel, (unsigned)div_up64(pu.rtotal, 256), 256, 0, st, sortedK, R, (const u32*)dir_shifted,
+                               dir_shift, (const u64*)kq, pu.rtotal, (u32)sa_off, rk);
+                    SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
+                }
+                SAB_TRY(sab_comm_exchange_back(cm, st, pu, rk, back, sizeof(u32)));
+                if (nu) {
+                    SAB_LAUNCH(dist_lazy_fill_kernel, (unsigned)div_up64(nu, 256), 256, 0, st, (const u32*)sp, (const u32*)back, nu,
+                               (const u32*)q, (u32)h, (u32)lo, ans, rank_local);
+                    SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
+                }
+                ph.mark(8);
+            }
+            u32* r2 = A.top<u32>(m + 8);
+            SAB_ARENA_CHECK(A);
+            SAB_TRY(sab_comm_exchange_back(cm, st, pr, ans, r2, sizeof(u32)));
+            if (m) {
+                SAB_LAUNCH(dist_place_keys_kernel, (unsigned)div_up64(m, 256), 256, 0, st, (const u32*)r1buf, (const u32*)ppart,
+                           (const u32*)r2, m, rb.k[rb.cur]);
+                SAB_LAUNCH_CHECK();
+                S.kernel_launches++;
+            }
+            A.hi = topmark;  // requests, answers and look-up buffers are dead (stream order)
+
+            // c. order inside the groups (as on one GPU: the list is still grouped by r1, ascending)
+            ph.mark(10);
+            u64 kept = 0;
+            u32* upd_idx = A.top<u32>(m + 8);
+            u32* upd_r = A.top<u32>(m + 8);
+            SAB_ARENA_CHECK(A);
+            if (m) {
+                SortBuffers<u64> sb;
+                sb.k[0] = rb.k[rb.cur];
+                sb.k[1] = rb.k[rb.cur ^ 1];
+                sb.v[0] = rb.v[rb.cur];
+                sb.v[1] = rb.v[rb.cur ^ 1];
+                sb.cur = 0;
+                int sorted = 0;
+                if (group_sort_on) {
+                    const u64 used = sab_align_up(m, 64);
+                    const u64 cap_keys = key_cap > used ? key_cap - used : 0;
+                    const u64 cap_vals = val_cap > used ? val_cap - used : 0;
+                    GroupSortSpare sp_;
+                    sp_.k[0] = sb.k[0] + used;
+                    sp_.k[1] = sb.k[1] + used;
+                    sp_.v[0] = sb.v[0] + used;
+                    sp_.v[1] = sb.v[1] + used;
+                    sp_.pos = r1buf;  // the first ranks live in the key words until the re-rank writes them back
+                    sp_.cap = cap_keys < cap_vals ? cap_keys : cap_vals;
+                    if (sp_.cap > val_cap) sp_.cap = val_cap;
+                    if (sp_.cap * 8 >= m) {
+                        u64 nbig = 0;
+                        sorted = sab_group_sort(c, sb, m, 32 + rank_bits, sp_, &S.passes[round], &nbig);
+                        if (sorted < 0) return sorted;
+                        if (nbig * 2 > m) group_sort_on = false;
+                    }
+                }
+                if (!sorted) SAB_TRY(sab_radix_sort<u64>(c, sb, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+                // d. re-rank; newly unique suffixes go to sa[], changed ranks are collected for their owners
+                ph.mark(11);
+                u32* out_idx = (sb.cur == 0) ? rb.v[rb.cur ^ 1] : rb.v[rb.cur];
+                const u64 tiles = div_up64(m, SAB_SCAN_TILE);
+                TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
+                sab_prof_begin(c, 3);
+                SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)sb.k[sb.cur], (const u32*)sb.v[sb.cur], m,
+                           (u32*)nullptr, sa_shifted, r1buf, out_idx, upd_idx, upd_r, (u32*)nullptr, d_m, ts);
+                sab_prof_end(c);
+                SAB_LAUNCH_CHECK();
+                S.kernel_launches++;
+                SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                SAB_CUDA_TRY(cudaStreamSynchronize(st));
+                kept = c->h_small[0];
+                if (sb.cur != 0 && kept > 0)
+                    SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1], rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            }
+            // e. changed ranks to their owners
+            ph.mark(12);
+            SAB_TRY(R_.send_ranks(upd_idx, upd_r, m));
+            A.hi = topmark;
+            rb.cur ^= 1;
+            m = kept;
+            u64 t1 = m;
+            SAB_TRY(sab_comm_sum_u64(cm, st, &t1, 1));
+            tot = t1;
+            S.active[round] = m;
+            ds->active[round] = tot;
+            h *= 2;
+        }
+    }
+    ph.mark(-1);
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    *n_active = c->h_small[0];
+    ph.collect(ds->phase_ms, &ds->total_ms);
+    S.rounds = round;
+    S.total_ms = ds->total_ms;
+    res->d_slice = sa_local;
+    res->slice_len = R;
+    res->sa_off = sa_off;
+    ds->rounds = round;
+    ds->lazy_isa = lazy ? 1u : 0u;
+    ds->rank_layout = (u32)layout_cyc;
+    ds->rebalanced = rebalanced ? 1u : 0u;
+    ds->slice_len = R;
+    ds->sa_off = sa_off;
+    ds->all_to_all_bytes = cm->bytes_sent;
+    ds->collectives = cm->collectives;
     return SAB_OK;
 }
 
-extern "C" int32_t sab200_dist_partition_owner(const uint32_t* d_key, const uint32_t* d_val, uint64_t count, uint32_t add,
-                                               uint32_t B, int32_t P, int32_t cyc_shift, uint32_t* d_key_out,
-                                               uint32_t* d_val_out, uint64_t* counts, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    OwnerDigit dop;
-    dop.add = add;
-    if (P > SAB_MAX_RANKS || !counts || sab_rank_layout(B, P, cyc_shift, &dop.lay) != 0) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, d_key, count, dop, P, counts)));
-    if (count) {
-        constexpr int TILE = PassShape<u32>::THREADS * PassShape<u32>::ITEMS;
-        SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
-        SAB_TRY((sab_launch_pass_op<u32, false, OwnerDigit>(c, d_key, d_key_out, d_val, d_val_out, count, dop, c->d_gbase)));
+// ------------------------------------------------------------------ extern "C": communicators
+extern "C" int32_t sab200_comm_unique_id(uint8_t id[128]) {
+#ifndef SAB_EMU
+    if (!id) return SAB_ERR_ARGS;
+    SAB_TRY(sab_nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    SAB_NCCL_TRY(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return SAB_OK;
+#else
+    (void)id;
+    sab_set_error("the emulator build has no NCCL");
+    return SAB_ERR_NCCL;
+#endif
+}
+
+extern "C" sab200_comm* sab200_comm_create_nccl(const uint8_t id[128], int32_t rank, int32_t nranks, int32_t device) {
+#ifndef SAB_EMU
+    if (!id || nranks < 1 || nranks > SAB_MAX_RANKS || rank < 0 || rank >= nranks) {
+        sab_set_error("sab200_comm_create_nccl: bad arguments (rank %d of %d)", (int)rank, (int)nranks);
+        return nullptr;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_partition_slices(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count,
-                                                const uint32_t* slice_start, int32_t P, uint32_t* d_pos_out,
-                                                uint32_t* d_val_out, uint64_t* counts, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (P < 1 || P > SAB_MAX_RANKS || !slice_start || !counts) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    SliceDigit dop;
-    for (int i = 0; i < SAB_MAX_RANKS; ++i) dop.start[i] = i < P ? slice_start[i] : 0xffffffffu;
-    dop.pmax = (u32)P - 1;
-    SAB_TRY((sab_count_and_base<u32, SliceDigit>(c, d_pos, count, dop, P, counts)));
-    if (count) {
-        constexpr int TILE = PassShape<u32>::THREADS * PassShape<u32>::ITEMS;
-        SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
-        SAB_TRY((sab_launch_pass_op<u32, false, SliceDigit>(c, d_pos, d_pos_out, d_val, d_val_out, count, dop, c->d_gbase)));
+    if (sab_nccl_load() != SAB_OK) return nullptr;
+    if (!sab_get_context(device)) return nullptr;
+    sab200_comm* cm = new (std::nothrow) sab200_comm();
+    if (!cm) return nullptr;
+    cm->rank = rank;
+    cm->P = nranks;
+    cm->device = device;
+    cm->kind = 0;
+    memset(&cm->cb, 0, sizeof(cm->cb));
+    memset(&cm->last, 0, sizeof(cm->last));
+    if (cudaSetDevice(device) != cudaSuccess || sab_comm_alloc_scratch(cm) != SAB_OK) {
+        sab_comm_free(cm);
+        return nullptr;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_scatter(const uint32_t* d_pos, const uint32_t* d_val, uint64_t count, uint32_t lo, uint32_t B,
-                                       int32_t P, int32_t cyc_shift, uint32_t* d_rank_local, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    RankLayout lay;
-    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        SAB_LAUNCH(dist_scatter_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, d_val, count, lo, lay, d_rank_local);
-        SAB_LAUNCH_CHECK();
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclComm_t nc = nullptr;
+    ncclResult_t r = g_nccl.CommInitRank(&nc, nranks, u, rank);
+    if (r != ncclSuccess) {
+        sab_set_error("ncclCommInitRank(rank %d of %d): %s", (int)rank, (int)nranks, g_nccl.GetErrorString(r));
+        sab_comm_free(cm);
+        return nullptr;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
+    cm->nccl = nc;
+    return cm;
+#else
+    (void)id; (void)rank; (void)nranks; (void)device;
+    sab_set_error("the emulator build has no NCCL");
+    return nullptr;
+#endif
 }
 
-extern "C" int32_t sab200_dist_gather(const uint32_t* d_pos, uint64_t count, uint32_t add, uint32_t lo, uint32_t B, int32_t P,
-                                      int32_t cyc_shift, const uint32_t* d_rank_local, uint32_t* d_out, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    RankLayout lay;
-    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        SAB_LAUNCH(dist_gather_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_pos, count, add, lo, lay, d_rank_local,
-                   d_out);
-        SAB_LAUNCH_CHECK();
+extern "C" sab200_comm* sab200_comm_create_callbacks(const sab200_comm_callbacks* cb, int32_t rank, int32_t nranks, int32_t device) {
+    if (!cb || !cb->all_gather || !cb->all_reduce_sum_u64 || !cb->all_to_all_v || nranks < 1 || nranks > SAB_MAX_RANKS || rank < 0 ||
+        rank >= nranks) {
+        sab_set_error("sab200_comm_create_callbacks: bad arguments (rank %d of %d)", (int)rank, (int)nranks);
+        return nullptr;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_make_keys(const uint32_t* d_r1, const uint32_t* d_r2, uint64_t count, uint64_t* d_key64,
-                                         int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        SAB_LAUNCH(dist_make_keys_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_r1, d_r2, count, d_key64);
-        SAB_LAUNCH_CHECK();
+    if (!sab_get_context(device)) return nullptr;
+    sab200_comm* cm = new (std::nothrow) sab200_comm();
+    if (!cm) return nullptr;
+    cm->rank = rank;
+    cm->P = nranks;
+    cm->device = device;
+    cm->kind = 1;
+    cm->cb = *cb;
+    memset(&cm->last, 0, sizeof(cm->last));
+    if (sab_comm_alloc_scratch(cm) != SAB_OK) {
+        sab_comm_free(cm);
+        return nullptr;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return cm;
+}
+
+extern "C" void sab200_comm_destroy(sab200_comm* cm) { sab_comm_free(cm); }
+
+extern "C" int32_t sab200_comm_stats(sab200_comm* cm, sab200_dist_stats* out) {
+    if (!cm || !out) return SAB_ERR_ARGS;
+    *out = cm->last;
     return SAB_OK;
 }
 
-extern "C" int32_t sab200_dist_rerank(const uint64_t* d_key64, const uint32_t* d_idx, uint64_t m, uint32_t sa_off,
-                                      uint32_t* d_sa_local, uint32_t* d_out_r1, uint32_t* d_out_idx, uint32_t* d_upd_idx,
-                                      uint32_t* d_upd_r, uint32_t* d_set_pos, uint64_t* n_kept, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (!n_kept) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    *n_kept = 0;
-    if (m == 0) return SAB_OK;
-    cudaStream_t st = c->stream;
-    const u64 tiles = div_up64(m, SAB_SCAN_TILE);
-    SAB_TRY(sab_ensure_scan(c, (size_t)tiles));
-    TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
-    u32* d_m = c->d_counters;
-    // ranks are global SA positions: index the local slice through a pointer shifted by the slice offset
-    u32* sa_shifted = d_sa_local - (size_t)sa_off;
-    SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, d_key64, d_idx, m, (u32*)nullptr, sa_shifted, d_out_r1,
-               d_out_idx, d_upd_idx, d_upd_r, d_set_pos, d_m, ts);
-    SAB_LAUNCH_CHECK();
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    *n_kept = c->h_small[0];
-    return SAB_OK;
-}
-
-// ------------------------------------------------------------------ lazy inverse suffix array, distributed
-// As on one GPU (sab_saca.cuh, step 5) only the ranks of ACTIVE suffixes are stored at their owners; rank[]
-// starts EMPTY.  A request that finds EMPTY at the owner concerns a suffix that was unique after the initial
-// sort: the owner re-packs its key from its text shard (lazy_collect), the key travels to the GPU whose
-// slice holds it (same splitters as the key exchange), that GPU finds it in its sorted keys (lower_bound:
-// rank = slice offset + index) and the rank travels back to be stored and answered (lazy_fill).
-__global__ void __launch_bounds__(256)
-dist_lazy_collect_kernel(const u32* __restrict__ q, const u32* __restrict__ ans, u64 count, u32 h, u64 shard_lo,
-                         const u8* __restrict__ text, u64 n_rel, const u16* __restrict__ lut, u32 base, int k,
-                         u64* __restrict__ keys_out, u32* __restrict__ slot_out, u32* __restrict__ counter) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count || ans[t] != 0xffffffffu) return;
-    const u32 p = atomicAdd(counter, 1u);
-    keys_out[p] = pack_key_at(text, n_rel, lut, base, k, (u64)q[t] + h - shard_lo);
-    slot_out[p] = (u32)t;
-}
-__global__ void __launch_bounds__(256)
-dist_lower_bound_kernel(const u64* __restrict__ sorted, u64 R, const u64* __restrict__ keys, u64 count, u32 sa_off,
-                        u32* __restrict__ rank_out) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const u64 key = keys[t];
-    u64 lo = 0, hi = R;
-    while (lo < hi) {
-        const u64 mid = lo + (hi - lo) / 2;
-        if (sorted[mid] < key) lo = mid + 1;
-        else hi = mid;
+// ------------------------------------------------------------------ one rank of a sharded construction
+// host_out_base != null: the slice is copied to host_out_base + sa_off (the caller's whole sa[] array)
+static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 n, int shard_on_device, u32* out, u64 out_cap,
+                           int out_on_device, u32* host_out_base, u64* slice_len, u64* sa_off, const u32** d_slice) {
+    if (!cm || (shard_len > 0 && !shard) || n > SAB200_MAX_LENGTH) {
+        sab_set_error("sab200_saca_sharded: bad arguments (n=%llu)", (unsigned long long)n);
+        return SAB_ERR_ARGS;
     }
-    // the key of a suffix that was unique after the initial sort is present exactly once
-    rank_out[t] = (lo < R && sorted[lo] == key) ? sa_off + (u32)lo : 0xffffffffu;
-}
-__global__ void __launch_bounds__(256)
-dist_lazy_fill_kernel(const u32* __restrict__ slot, const u32* __restrict__ rank, u64 count, const u32* __restrict__ q, u32 h,
-                      u32 lo, u32* __restrict__ ans, u32* __restrict__ rank_local) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const u32 s = slot[t], r = rank[t];
-    ans[s] = r;
-    rank_local[(u64)q[s] + h - lo] = r;  // memoised: the next request for this position is answered directly
-}
-
-extern "C" int32_t sab200_dist_lazy_collect(const uint32_t* d_q, const uint32_t* d_ans, uint64_t count, uint32_t h,
-                                            uint64_t shard_lo, const uint8_t* d_text, uint64_t n, const uint16_t* lut256,
-                                            int32_t b, int32_t k, uint64_t* d_keys_out, uint32_t* d_slot_out,
-                                            uint64_t* n_unresolved, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (!n_unresolved || !lut256 || shard_lo > n || b < 2 || k < 1 || k > 64) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    *n_unresolved = 0;
-    if (count == 0) return SAB_OK;
-    cudaStream_t st = c->stream;
-    u16* d_lut = (u16*)(c->d_counters + 16 + 256);
-    memcpy(c->h_small + 384, lut256, 256 * sizeof(u16));
-    SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, 256 * sizeof(u16), cudaMemcpyHostToDevice, st));
-    u32* d_cnt = c->d_counters + 12;
-    SAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(u32), st));
-    SAB_LAUNCH(dist_lazy_collect_kernel, (unsigned)div_up64(count, 256), 256, 0, st, d_q, d_ans, count, h, shard_lo, d_text,
-               n - shard_lo, (const u16*)d_lut, (u32)b, (int)k, d_keys_out, d_slot_out, d_cnt);
-    SAB_LAUNCH_CHECK();
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 12, d_cnt, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    *n_unresolved = c->h_small[12];
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_lower_bound(const uint64_t* d_sorted_keys, uint64_t R, const uint64_t* d_keys, uint64_t count,
-                                           uint32_t sa_off, uint32_t* d_rank_out, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
+    SabContext* c = sab_get_context(cm->device);
     if (!c) return SAB_ERR_CUDA;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        SAB_LAUNCH(dist_lower_bound_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_sorted_keys, R, d_keys, count,
-                   sa_off, d_rank_out);
-        SAB_LAUNCH_CHECK();
-    }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_lazy_fill(const uint32_t* d_slot, const uint32_t* d_rank, uint64_t count, const uint32_t* d_q,
-                                         uint32_t h, uint32_t lo, uint32_t* d_ans, uint32_t* d_rank_local, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        SAB_LAUNCH(dist_lazy_fill_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_slot, d_rank, count, d_q, h, lo,
-                   d_ans, d_rank_local);
-        SAB_LAUNCH_CHECK();
-    }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-// Bracket a multi-GPU construction on this rank: begin() clears the counters (and arms the per-launch
-// events when profiling is on); end() collects them into the record sab200_get_stats() returns.
-extern "C" int32_t sab200_dist_begin(int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
     memset(&c->stats, 0, sizeof(c->stats));
     c->profiling = g_profiling;
-    return SAB_OK;
-}
-extern "C" int32_t sab200_dist_end(int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    std::lock_guard<std::mutex> lk(c->mu);
+    sab200_dist_stats& ds = cm->last;
+    memset(&ds, 0, sizeof(ds));
+    const u64 B = n ? div_up64(n, (u64)cm->P) : 1;
+    SAB_TRY(sab_dist_reserve(c, B));
+    DistArena A;
+    A.base = c->arena;
+    A.lo = 0;
+    A.hi = c->arena_bytes & ~(size_t)255;
+    A.ok = true;
+    cudaStream_t st = c->stream;
+    const u8* d_text = shard;
+    cudaEvent_t e0 = sab_event_get(c), e1 = sab_event_get(c), e2 = sab_event_get(c), e3 = sab_event_get(c);
+    cudaEventRecord(e0, st);
+    if (!shard_on_device) {
+        u8* t = A.bot<u8>((size_t)shard_len + 64);
+        SAB_ARENA_CHECK(A);
+        if (shard_len) SAB_CUDA_TRY(cudaMemcpyAsync(t, shard, shard_len, cudaMemcpyHostToDevice, st));
+        d_text = t;
+    }
+    cudaEventRecord(e1, st);
+    DistResult res;
+    int rc = sab_dist_saca(cm, c, A, d_text, shard_len, n, &res, &ds);
+    if (rc != SAB_OK) {
+        cudaMemsetAsync(c->d_ticket, 0, sizeof(u32) * 4, st);  // a failed launch may have left the ticket out of step
+        cudaStreamSynchronize(st);
+        c->ticket_host = 0;
+        return rc;
+    }
+    if (slice_len) *slice_len = res.slice_len;
+    if (sa_off) *sa_off = res.sa_off;
+    if (d_slice) *d_slice = res.d_slice;
+    cudaEventRecord(e2, st);
+    if (host_out_base) {
+        if (res.slice_len)
+            SAB_CUDA_TRY(cudaMemcpyAsync(host_out_base + res.sa_off, res.d_slice, res.slice_len * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (cm->rank == 0) {
+            c->h_small[32] = (u32)n;
+            memcpy(host_out_base, c->h_small + 32, sizeof(u32));  // sa[0] = n (src/saca.rs:13)
+        }
+    } else if (out) {
+        if (out_cap < res.slice_len) {
+            sab_set_error("sab200_saca_sharded: the slice has %llu entries, the buffer holds %llu", (unsigned long long)res.slice_len,
+                          (unsigned long long)out_cap);
+            return SAB_ERR_ARGS;
+        }
+        if (res.slice_len)
+            SAB_CUDA_TRY(cudaMemcpyAsync(out, res.d_slice, res.slice_len * sizeof(u32),
+                                         out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    cudaEventRecord(e3, st);
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ds.phase_ms[14] = ms;
+    cudaEventElapsedTime(&ms, e2, e3);
+    ds.phase_ms[15] = ms;
+    c->stats.h2d_ms = ds.phase_ms[14];
+    c->stats.d2h_ms = ds.phase_ms[15];
+    c->event_pool.push_back(e0);
+    c->event_pool.push_back(e1);
+    c->event_pool.push_back(e2);
+    c->event_pool.push_back(e3);
     sab_prof_collect(c);
     g_last_stats = c->stats;
     return SAB_OK;
 }
 
-// ------------------------------------------------------------------ peer-to-peer rank array (NVLink)
-// With the per-rank blocks of rank[] mapped into every process (symmetric memory), a round needs no
-// exchange step at all: the gather kernel loads rank[i+h] straight from the owner GPU over NVLink and
-// the changed ranks are stored straight into the owner's block.  The host only orders the phases
-// (every rank has finished reading before anyone writes, and vice versa).
-struct PeerTable {
-    u32* p[SAB_MAX_RANKS];
-};
-
-// key64[t] = (r1[t] << 32) | rank[idx[t] + h], rank[] distributed over the GPUs as `lay` says
-__global__ void __launch_bounds__(256)
-dist_gather_p2p_kernel(const u32* __restrict__ r1, const u32* __restrict__ idx, u64 m, u32 h, RankLayout lay, PeerTable pt,
-                       u64* __restrict__ key64) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    const u64 q = (u64)idx[t] + h;
-    const u32 o = lay.owner(q);
-    const u32 r2 = pt.p[o][lay.slot(q, o)];
-    key64[t] = ((u64)r1[t] << 32) | r2;
-}
-
-// rank[idx[t]] = val[t] on the owner of idx[t]; idx == 0xFFFFFFFF marks "nothing to write"
-__global__ void __launch_bounds__(256)
-dist_scatter_p2p_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 count, RankLayout lay, PeerTable pt) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const u32 i = idx[t];
-    if (i == 0xffffffffu) return;
-    const u32 o = lay.owner(i);
-    pt.p[o][lay.slot(i, o)] = val[t];
-}
-
-static int sab_peer_table(const uint64_t* peer_ptrs, int32_t P, PeerTable* pt) {
-    if (!peer_ptrs || P < 1 || P > SAB_MAX_RANKS) return SAB_ERR_ARGS;
-    for (int i = 0; i < SAB_MAX_RANKS; ++i) pt->p[i] = i < P ? (u32*)(uintptr_t)peer_ptrs[i] : nullptr;
+extern "C" int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device) {
+    if (!dst || !d_src) return bytes ? SAB_ERR_ARGS : SAB_OK;
+    SabContext* c = sab_get_context(device);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    SAB_CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SAB_OK;
 }
 
-extern "C" int32_t sab200_dist_gather_p2p(const uint32_t* d_r1, const uint32_t* d_idx, uint64_t m, uint32_t h, uint32_t B,
-                                          int32_t P, int32_t cyc_shift, const uint64_t* peer_rank_ptrs, uint64_t* d_key64,
-                                          int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    PeerTable pt;
-    SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
-    RankLayout lay;
-    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (m) {
-        sab_prof_begin(c, 4);
-        SAB_LAUNCH(dist_gather_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, c->stream, d_r1, d_idx, m, h, lay, pt, d_key64);
-        sab_prof_end(c);
-        SAB_LAUNCH_CHECK();
-        c->stats.kernel_launches++;
+extern "C" int32_t sab200_saca_sharded(sab200_comm* cm, const uint8_t* shard, uint64_t shard_len, uint64_t n, int32_t shard_on_device,
+                                       uint32_t* out, uint64_t out_cap, int32_t out_on_device, uint64_t* slice_len,
+                                       uint64_t* sa_off, const uint32_t** d_slice) {
+    return sab_sharded_run(cm, shard, shard_len, n, shard_on_device, out, out_cap, out_on_device, nullptr, slice_len, sa_off, d_slice);
+}
+
+// ------------------------------------------------------------------ one process, ngpus GPUs: sab200_saca(..., ngpus > 1)
+static std::mutex g_multi_mu;
+static std::vector<sab200_comm*> g_multi_comms;  // ncclCommInitAll over devices 0..P-1, cached between calls
+
+static int sab_multi_comms(int P) {
+#ifndef SAB_EMU
+    if ((int)g_multi_comms.size() == P) return SAB_OK;
+    for (auto* cm : g_multi_comms) sab_comm_free(cm);
+    g_multi_comms.clear();
+    SAB_TRY(sab_nccl_load());
+    std::vector<int> devs(P);
+    for (int i = 0; i < P; ++i) {
+        devs[i] = i;
+        if (!sab_get_context(i)) return SAB_ERR_CUDA;
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-extern "C" int32_t sab200_dist_scatter_p2p(const uint32_t* d_idx, const uint32_t* d_val, uint64_t count, uint32_t B, int32_t P,
-                                           int32_t cyc_shift, const uint64_t* peer_rank_ptrs, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    PeerTable pt;
-    SAB_TRY(sab_peer_table(peer_rank_ptrs, P, &pt));
-    RankLayout lay;
-    if (sab_rank_layout(B, P, cyc_shift, &lay) != 0) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count) {
-        sab_prof_begin(c, 3);
-        SAB_LAUNCH(dist_scatter_p2p_kernel, (unsigned)div_up64(count, 256), 256, 0, c->stream, d_idx, d_val, count, lay, pt);
-        sab_prof_end(c);
-        SAB_LAUNCH_CHECK();
-        c->stats.kernel_launches++;
+    std::vector<ncclComm_t> nc(P);
+    SAB_NCCL_TRY(g_nccl.CommInitAll(nc.data(), P, devs.data()));
+    for (int i = 0; i < P; ++i) {
+        sab200_comm* cm = new (std::nothrow) sab200_comm();
+        if (!cm) return SAB_ERR_OOM;
+        cm->rank = i;
+        cm->P = P;
+        cm->device = i;
+        cm->kind = 0;
+        cm->nccl = nc[i];
+        memset(&cm->cb, 0, sizeof(cm->cb));
+        memset(&cm->last, 0, sizeof(cm->last));
+        g_multi_comms.push_back(cm);
+        SAB_TRY(sab_comm_alloc_scratch(cm));
     }
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SAB_OK;
+#else
+    (void)P;
+    sab_set_error("the emulator build has no NCCL");
+    return SAB_ERR_NCCL;
+#endif
 }
 
-// ------------------------------------------------------------------ key exchange fused into the partition
-// counts only (host, P x u64): how many of the keys go to each destination
-extern "C" int32_t sab200_dist_count_keys(const uint64_t* d_keys, uint64_t count, const uint64_t* splitters, int32_t nsplit,
-                                          uint64_t* counts, int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (nsplit < 0 || nsplit > SAB_MAX_RANKS - 1 || !counts) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    SplitterDigit dop;
-    dop.np = nsplit;
-    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) dop.s[i] = i < nsplit ? splitters[i] : ~0ull;
-    SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, d_keys, count, dop, nsplit + 1, counts)));
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return SAB_OK;
-}
-
-// The partition pass writes destination d's records straight into GPU d's receive buffers
-// (peer_key_ptrs[d], peer_idx_ptrs[d]: device addresses mapped into this process) starting at record
-// offsets[d] (= records the lower ranks send to d): partition and all-to-all in one kernel, the
-// transfer overlapping the ranking tile by tile.  The caller barriers before reading the buffers.
-extern "C" int32_t sab200_dist_partition_keys_p2p(const uint64_t* d_keys, const uint32_t* d_idx, uint64_t count,
-                                                  const uint64_t* splitters, int32_t nsplit, const uint64_t* offsets,
-                                                  const uint64_t* peer_key_ptrs, const uint64_t* peer_idx_ptrs,
-                                                  int32_t device) {
-    SabContext* c = sab_dist_ctx(device);
-    if (!c) return SAB_ERR_CUDA;
-    if (nsplit < 0 || nsplit > SAB_MAX_RANKS - 1 || !offsets || !peer_key_ptrs || !peer_idx_ptrs) return SAB_ERR_ARGS;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (count == 0) return SAB_OK;
-    SplitterDigit dop;
-    dop.np = nsplit;
-    for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) dop.s[i] = i < nsplit ? splitters[i] : ~0ull;
-    PeerOut po;
-    memset(&po, 0, sizeof(po));
-    u64* h = (u64*)(c->h_small + 1024);
-    for (int i = 0; i < 256; ++i) h[i] = 0;
-    for (int d = 0; d <= nsplit; ++d) {
-        po.k[d] = peer_key_ptrs[d];
-        po.v[d] = peer_idx_ptrs[d];
-        h[d] = offsets[d];
+static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    SAB_TRY(sab_multi_comms(P));
+    std::vector<int> rcs(P, SAB_OK);
+    std::vector<std::thread> th;
+    const u64 B = n ? div_up64(n, (u64)P) : 1;
+    for (int g = 0; g < P; ++g) {
+        th.emplace_back([&, g]() {
+            const u64 lo = (u64)g * B < n ? (u64)g * B : n;
+            const u64 hi = lo + B < n ? lo + B : n;
+            const u64 len = (n - lo) < (hi - lo) + SAB200_SHARD_HALO ? (n - lo) : (hi - lo) + SAB200_SHARD_HALO;
+            rcs[g] = sab_sharded_run(g_multi_comms[g], s + lo, len, n, 0, nullptr, 0, 0, sa, nullptr, nullptr, nullptr);
+        });
     }
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->d_gbase, h, 256 * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    constexpr int TILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
-    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(count, TILE)));
-    SAB_TRY((sab_launch_pass_op<u64, false, SplitterDigit, true>(c, d_keys, (u64*)nullptr, d_idx, (u32*)nullptr, count, dop,
-                                                                  c->d_gbase, &po)));
-    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (auto& t : th) t.join();
+    if (n == 0) sa[0] = 0;
+    for (int g = 0; g < P; ++g)
+        if (rcs[g] != SAB_OK) return rcs[g];
     return SAB_OK;
+}
+
+extern "C" int32_t sab200_multi_stats(int32_t rank, sab200_dist_stats* out) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    if (!out || rank < 0 || rank >= (int)g_multi_comms.size()) return SAB_ERR_ARGS;
+    *out = g_multi_comms[rank]->last;
+    return SAB_OK;
+}
+
+static void sab_multi_shutdown() {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    for (auto* cm : g_multi_comms) sab_comm_free(cm);
+    g_multi_comms.clear();
 }

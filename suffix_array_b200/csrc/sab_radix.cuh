@@ -232,12 +232,12 @@ struct PeerOut {
     u64 v[SAB_MAX_RANKS];  // payload buffer of every destination
 };
 
-// vals_in may be null when IOTA_VAL (payload = position of the record in the input).
+// vals_in may be null when IOTA_VAL (payload = iota_base + position of the record in the input).
 template <typename KeyT, typename DigitOp, bool HAS_VAL, bool IOTA_VAL, bool PEER, int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, SAB_ONESWEEP_MIN_BLOCKS)
 onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, const u32* __restrict__ vals_in,
                 u32* __restrict__ vals_out, u64 n, DigitOp dop, const u64* __restrict__ gbase,
-                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch, PeerOut po) {
+                u64* __restrict__ lookback, u32* __restrict__ ticket, u32 ticket_base, u32 epoch, PeerOut po, u32 iota_base) {
     typedef OnesweepCfg<KeyT, HAS_VAL, IOTA_VAL, THREADS, ITEMS> Cfg;
     static_assert(THREADS >= SAB_RADIX_BINS && THREADS % 32 == 0, "one look-back lane per bin");
     constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE, WTILE = 32 * ITEMS;
@@ -279,7 +279,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         for (int k = 0; k < ITEMS; ++k) keys[k] = kin[k * 32];
         if (HAS_VAL) {
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) vals[k] = IOTA_VAL ? (u32)(tile_base + wofs + k * 32) : vin[k * 32];
+            for (int k = 0; k < ITEMS; ++k) vals[k] = IOTA_VAL ? iota_base + (u32)(tile_base + wofs + k * 32) : vin[k * 32];
         }
     } else {
 #pragma unroll
@@ -287,7 +287,7 @@ onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out, c
         if (HAS_VAL) {
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
-                if (IOTA_VAL) vals[k] = (u32)(tile_base + wofs + k * 32);
+                if (IOTA_VAL) vals[k] = iota_base + (u32)(tile_base + wofs + k * 32);
                 else vals[k] = (wofs + k * 32 < valid) ? vin[k * 32] : 0u;
             }
         }

@@ -154,22 +154,30 @@ struct LazyIsa {
     int k, dir_shift;
 };
 
-__device__ __forceinline__ u32 lazy_rank_lookup(const LazyIsa& z, u64 t) {
-    const u64 key = pack_key_at(z.text, z.n, z.lut, z.base, z.k, t);
-    u64 lo = z.dir[key >> z.dir_shift];
+// index of the first record of sorted_keys[0..cnt) whose key is >= key, starting from the directory entry
+// of the key's bucket (dir is indexed by key >> dir_shift; callers pre-offset the pointer when the array
+// only covers a slice of the key space)
+__device__ __forceinline__ u64 sorted_key_position(const u64* __restrict__ sorted_keys, u64 cnt, const u32* __restrict__ dir,
+                                                   int dir_shift, u64 key) {
+    u64 lo = dir[key >> dir_shift];
     u64 hi = lo, step = 1;
-    while (hi < z.n && z.sorted_keys[hi] < key) {  // gallop: keys[lo-1] < key stays true
+    while (hi < cnt && sorted_keys[hi] < key) {  // gallop: keys[lo-1] < key stays true
         lo = hi + 1;
         hi += step;
         step <<= 1;
     }
-    if (hi > z.n) hi = z.n;
-    while (lo < hi) {  // first position whose key is >= key; the key of t is present exactly once
+    if (hi > cnt) hi = cnt;
+    while (lo < hi) {  // first position whose key is >= key; the key looked up is present exactly once
         const u64 mid = lo + (hi - lo) / 2;
-        if (z.sorted_keys[mid] < key) lo = mid + 1;
+        if (sorted_keys[mid] < key) lo = mid + 1;
         else hi = mid;
     }
-    return (u32)lo + 1u;
+    return lo;
+}
+
+__device__ __forceinline__ u32 lazy_rank_lookup(const LazyIsa& z, u64 t) {
+    const u64 key = pack_key_at(z.text, z.n, z.lut, z.base, z.k, t);
+    return (u32)sorted_key_position(z.sorted_keys, z.n, z.dir, z.dir_shift, key) + 1u;
 }
 
 // rank[I[j]] = j + 1 for every singleton record (complete-ISA fallback)

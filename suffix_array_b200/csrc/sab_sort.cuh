@@ -30,7 +30,7 @@ struct PassShape<u32> {
 
 template <typename KeyT, bool IOTA, typename DigitOp, bool PEER = false>
 static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const u32* vin, u32* vout, u64 n, DigitOp dop,
-                              const u64* gbase, const PeerOut* peer = nullptr) {
+                              const u64* gbase, const PeerOut* peer = nullptr, u32 iota_base = 0) {
     constexpr int THREADS = PassShape<KeyT>::THREADS, ITEMS = PassShape<KeyT>::ITEMS;
     typedef OnesweepCfg<KeyT, true, IOTA, THREADS, ITEMS> Cfg;
     const u64 tiles = div_up64(n, (u64)Cfg::TILE);
@@ -48,7 +48,7 @@ static int sab_launch_pass_op(SabContext* c, const KeyT* kin, KeyT* kout, const 
 #endif
     sab_prof_begin(c, 0);
     SAB_LAUNCH(kern, (unsigned)tiles, THREADS, Cfg::SMEM, c->stream, kin, kout, vin, vout, n, dop, gbase,
-               c->d_lookback, c->d_ticket, c->ticket_host, epoch, po);
+               c->d_lookback, c->d_ticket, c->ticket_host, epoch, po, iota_base);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     c->ticket_host += (u32)tiles;

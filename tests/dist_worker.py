@@ -1,6 +1,10 @@
-"""Worker of tests/test_dist_gloo.py: one rank of the multi-GPU construction driver
-(suffix_array_b200/dist.py) on CPU -- gloo collectives, the SIMT-emulator build as the "device" --
-compared bit-exactly with the oracle.  Launched through torch.distributed.run."""
+"""Worker of tests/test_dist_gloo.py and tests/test_gpu_multi.py: one rank of the multi-GPU construction
+(libsab200's distributed driver through suffix_array_b200.dist.Comm), assembled suffix array compared
+bit-exactly with the oracle.  Launched through torch.distributed.run.
+
+  SAB_DIST_BACKEND=gloo  (default) CPU: the SIMT-emulator build as the "device", the collectives handed to the
+                         library as callbacks over gloo
+  SAB_DIST_BACKEND=nccl  real GPUs, real library, NCCL inside the library"""
 import ctypes
 import os
 import sys
@@ -23,15 +27,15 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        device = "cuda:%d" % local
         _lib.require_gpu()
+        comm = sdist.Comm("nccl", device="cuda:%d" % local)
         big = [gen.dna_like(24 << 20), gen.mixed(16 << 20), gen.repetitive(8 << 20, block=1 << 14), gen.uniform_bytes(16 << 20),
                np.full(1 << 20, 65, dtype=np.uint8)]
     else:
         dist.init_process_group("gloo")
-        device = "cpu"
-        emu = _lib._bind(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libsab200_emu.so")))
+        emu = _lib._bind(ctypes.CDLL(os.path.join(ROOT, "tests", "emu", os.environ.get("SAB_EMU_LIB", "libsab200_emu.so"))))
         _lib._lib = emu  # test-only injection of the emulator build
+        comm = sdist.Comm("callbacks")
         big = []
     rank, world = dist.get_rank(), dist.get_world_size()
     cases = big + [np.frombuffer(b"", dtype=np.uint8), np.frombuffer(b"a", dtype=np.uint8), np.frombuffer(b"banana", dtype=np.uint8),
@@ -43,19 +47,20 @@ def main():
     for t in cases:
         n = int(t.size)
         B, lo, hi = sdist.shard_bounds(n, rank, world)
-        shard = t[lo:min(n, hi + sdist.HALO)]
-        st = {}
-        sa_local, sa_off = sdist.dist_saca(shard, n, device, stats=st, exchange=os.environ.get("SAB_DIST_EXCHANGE", "auto"))
+        shard = np.ascontiguousarray(t[lo:min(n, hi + sdist.HALO)])
+        sa_local, sa_off = comm.saca(shard, n)
+        st = comm.stats()
         full = sdist.gather_sa(sa_local, n)
         if rank == 0:
             exp = oracle.saca(t)
             good = bool(np.array_equal(full, exp))
-            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d exchange=%s rebalanced=%s layout=%s lazy=%s resolved=%d " % (
-                n, world, st["rounds"], good, st["all_to_all_bytes"], st["exchange"], st.get("rebalanced"), st.get("rank_layout"),
-                st.get("lazy_isa"), st.get("resolved_empty", 0)), flush=True)
+            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d collectives=%d rebalanced=%s layout=%s lazy=%s resolved=%d " % (
+                n, world, st["rounds"], good, st["all_to_all_bytes"], st["collectives"], bool(st["rebalanced"]),
+                "cyclic" if st["rank_layout"] else "block", bool(st["lazy_isa"]), st["resolved_empty"]), flush=True)
             ok = ok and good
-    flag = torch.tensor([1 if ok else 0], device=device)
+    flag = torch.tensor([1 if ok else 0], device="cuda" if backend == "nccl" else "cpu")
     dist.broadcast(flag, 0)
+    comm.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
