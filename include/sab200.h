@@ -192,6 +192,11 @@ typedef struct sab200_dist_stats {
     double phase_ms[SAB200_PHASES];     /* CUDA events on the rank's stream */
     double total_ms;
 } sab200_dist_stats;
+/* Building block, exported for tests and tools: stable LSD radix sort of `count` (u64 key, u32 payload) records by
+ * key bits [0, key_bits) over a double buffer of DEVICE memory on `device`.  Returns 0 / 1 = the buffer pair
+ * (d_k0, d_v0) / (d_k1, d_v1) that holds the result, < 0 on error. */
+int32_t sab200_sort_pairs_device(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
+                                 int32_t key_bits, int32_t device);
 /* Copies `bytes` from the library's device arena on `device` (a d_slice pointer) into host memory. */
 int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device);
 /* counters of the last sharded construction on `comm` */

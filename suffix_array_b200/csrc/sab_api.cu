@@ -254,10 +254,13 @@ int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
         sab_set_error("sab200_saca: bad arguments (n=%llu, ngpus=%d)", (unsigned long long)n, (int)ngpus);
         return SAB_ERR_ARGS;
     }
-    if (ngpus < 1 || ngpus > sab200_device_count()) {
-        sab_set_error("sab200_saca: %d GPUs requested, %d visible; libsab200 has no CPU fallback", (int)ngpus,
-                      (int)sab200_device_count());
-        return ngpus < 1 ? SAB_ERR_CUDA : SAB_ERR_ARGS;
+    if (sab200_device_count() < 1) {
+        sab_set_error("no CUDA device available; libsab200 has no CPU fallback");
+        return SAB_ERR_CUDA;
+    }
+    if (ngpus > sab200_device_count()) {
+        sab_set_error("sab200_saca: %d GPUs requested, %d visible", (int)ngpus, (int)sab200_device_count());
+        return SAB_ERR_ARGS;
     }
     if (ngpus > 1) return sab_saca_multi(s, n, sa, ngpus);
     SabContext* c = sab_get_context(0);

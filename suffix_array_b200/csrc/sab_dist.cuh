@@ -871,6 +871,26 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     return SAB_OK;
 }
 
+extern "C" int32_t sab200_sort_pairs_device(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
+                                            int32_t key_bits, int32_t device) {
+    SabContext* c = sab_get_context(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (key_bits < 0 || key_bits > 64) return SAB_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    SortBuffers<u64> buf;
+    buf.k[0] = d_k0;
+    buf.k[1] = d_k1;
+    buf.v[0] = d_v0;
+    buf.v[1] = d_v1;
+    buf.cur = 0;
+    u32 passes = 0;
+    const int rc = sab_radix_sort<u64>(c, buf, count, 0, key_bits, false, &passes);
+    if (rc != SAB_OK) return rc;
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return buf.cur;
+}
+
 extern "C" int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device) {
     if (!dst || !d_src) return bytes ? SAB_ERR_ARGS : SAB_OK;
     SabContext* c = sab_get_context(device);

@@ -17,6 +17,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def planted(rng, n, sigma, seg, copies):
+    """Random text with `copies` mutated copies of one segment: few suffixes stay active after the initial sort
+    (lazy inverse suffix array), but they need several doubling rounds."""
+    t = rng.integers(0, sigma, n, dtype=np.uint8)
+    src = t[100:100 + seg].copy()
+    for c in range(copies):
+        at = int(rng.integers(2000, n - seg - 10))
+        t[at:at + seg] = src
+        t[at + int(rng.integers(0, seg))] ^= 1
+    return t
+
+
 def main():
     backend = os.environ.get("SAB_DIST_BACKEND", "gloo")
     from suffix_array_b200 import _lib, gen
@@ -42,7 +54,12 @@ def main():
              np.frombuffer(b"mississippi" * 7, dtype=np.uint8), np.full(3000, 97, dtype=np.uint8),
              np.frombuffer(b"\x00\xff" * 900 + b"\x00", dtype=np.uint8), gen.dna_like(20000), gen.uniform_bytes(9000),
              gen.repetitive(12000, block=257, mut_rate=2e-3), gen.mixed(7000),
-             rng.integers(0, 3, 5001, dtype=np.uint8)]
+             rng.integers(0, 3, 5001, dtype=np.uint8), planted(rng, 40000, 256, 1500, 4), planted(rng, 30000, 4, 900, 3)]
+    fuzz = int(os.environ.get("SAB_DIST_FUZZ", "0"))
+    if fuzz:  # fixed-seed randomized texts (runs, repeats with mutations, mixtures): same list on every rank
+        from tests import parity_cases as pc
+        frng = np.random.default_rng(int(os.environ.get("SAB_DIST_FUZZ_SEED", "7")))
+        cases = [pc.random_text(frng) for _ in range(fuzz)]
     ok = True
     for t in cases:
         n = int(t.size)

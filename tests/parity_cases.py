@@ -177,3 +177,24 @@ def check_pack(oracle, s):
                 raise AssertionError("suffix array of another text accepted")
             except ValueError:
                 pass
+
+
+def random_text(rng):
+    """Texts with structure: runs, repeats with mutations, mixtures of unique and repetitive regions."""
+    from suffix_array_b200 import gen
+    kind = int(rng.integers(0, 6))
+    n = int(rng.integers(1, 40000))
+    if kind == 0:
+        return rng.integers(0, int(rng.integers(1, 6)), n, dtype=np.uint8)
+    if kind == 1:
+        return gen.dna_like(n)
+    if kind == 2:
+        return gen.repetitive(n, block=int(rng.integers(8, 3000)), mut_rate=float(rng.choice([0, 1e-3, 1e-2, 1e-1])))
+    if kind == 3:
+        return gen.mixed_range(max(n, 64), 0, max(n, 64))
+    if kind == 4:
+        a = rng.integers(0, 256, n // 2 + 1, dtype=np.uint8)
+        b = np.tile(rng.integers(97, 101, int(rng.integers(3, 90)), dtype=np.uint8), n // 50 + 2)
+        return np.concatenate([a, b, a[:n // 5]])
+    base = gen.repetitive(max(n, 100), block=int(rng.integers(50, 1500)), mut_rate=float(rng.choice([1e-3, 1e-2])))
+    return np.concatenate([base, gen.dna_like(max(n // 3, 10)), base[:n // 2]])

@@ -1,5 +1,7 @@
-"""The N>1 construction path on CPU: world_size 2 and 3 over gloo, every kernel step running in the
-SIMT-emulator build, the assembled suffix array compared bit-exactly with the oracle."""
+"""The N>1 construction path on CPU: world_size 2 and 3 over gloo.  The distributed driver is the one inside
+libsab200 (csrc/sab_dist.cuh) compiled against the SIMT emulator; its collectives are handed in as callbacks
+(suffix_array_b200.dist.Comm("callbacks")) that run torch.distributed over gloo.  The assembled suffix array is
+compared bit-exactly with the oracle."""
 import os
 import subprocess
 import sys
@@ -9,32 +11,45 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,port,rebalance_min,layout", [(2, 29611, None, "block"), (3, 29612, None, "block"),
-                                                             (3, 29613, "0", "block"), (2, 29614, "0", "block"),
-                                                             (3, 29615, None, "cyclic"), (2, 29616, "0", "cyclic"),
-                                                             (3, 29617, "0", "lazy"), (2, 29618, None, "lazy")])
-def test_dist_construction_gloo(emu_lib, world, port, rebalance_min, layout):
-    """layout: distribution of rank[] over the ranks (block / block-cyclic).
-    rebalance_min="0": the active lists are evened out across the ranks whenever they are uneven, so newly
-    unique suffixes are routed to the owners of their suffix-array slices (the large-text path)."""
+def _run(world, port, env_extra, timeout=900):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
-    lazy = layout == "lazy"  # lazy inverse suffix array (block layout): only active ranks travel to their owners
-    layout = "block" if lazy else layout
-    env = dict(os.environ, OMP_NUM_THREADS="1", SAB_RANK_LAYOUT=layout, SAB_DIST_LAZY="1" if lazy else "0",
-               SAB_DIST_LAZY_MAX_ACTIVE="1.0")  # the emulator build keeps many suffixes active: take the lazy path anyway
-    if rebalance_min is not None:
-        env["SAB_REBALANCE_MIN"] = rebalance_min
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1", **env_extra)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("slices_ok=True") == 11, out.stdout
-    assert out.stdout.count("layout=" + layout) == 11, out.stdout
-    if lazy:
-        assert out.stdout.count("lazy=True") == 10, out.stdout  # every text but the empty one
-        resolved = [int(l.split("resolved=")[1].split()[0]) for l in out.stdout.splitlines() if "lazy=True" in l]
-        assert sum(1 for r in resolved if r > 0) >= 1, out.stdout
-    if rebalance_min == "0":
-        assert out.stdout.count("rebalanced=True") >= 2, out.stdout
+    return out.stdout
+
+
+@pytest.mark.parametrize("world,port,lib", [(2, 29611, "libsab200_emu.so"), (3, 29612, "libsab200_emu.so"),
+                                            (2, 29613, "libsab200_emu_prod.so"), (3, 29614, "libsab200_emu_prod.so")])
+def test_dist_construction_gloo(emu_lib, world, port, lib):
+    """lib: the plain emulator build keeps most suffixes active after the initial sort (complete inverse suffix
+    array, block-cyclic rank[] ownership); the build with the production cost-model constant leaves few
+    (lazy inverse suffix array: EMPTY look-ups resolved through the keys)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "suffix_array_b200", "csrc"), "emu-prod"], stdout=subprocess.DEVNULL)
+    out = _run(world, port, {"SAB_EMU_LIB": lib})
+    assert out.count("slices_ok=True") == 13, out
+    if lib.endswith("prod.so"):
+        assert out.count("lazy=True") >= 2, out
+        resolved = [int(l.split("resolved=")[1].split()[0]) for l in out.splitlines() if "lazy=True" in l]
+        assert sum(1 for r in resolved if r > 0) >= 1, out
+        deep = [int(l.split("rounds=")[1].split()[0]) for l in out.splitlines() if "lazy=True" in l]
+        assert max(deep) >= 4, out  # look-ups and memoised ranks over several rounds
+    else:
+        assert out.count("layout=cyclic") >= 5, out
+
+
+@pytest.mark.parametrize("world,port,lib,layout", [(2, 29615, "libsab200_emu_prod.so", None), (3, 29616, "libsab200_emu.so", "block")])
+def test_dist_randomized_gloo(emu_lib, world, port, lib, layout):
+    """Fixed-seed randomized texts (tests/parity_cases.random_text) through the distributed driver."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "suffix_array_b200", "csrc"), "emu-prod"], stdout=subprocess.DEVNULL)
+    env = {"SAB_EMU_LIB": lib, "SAB_DIST_FUZZ": "10"}
+    if layout:
+        env["SAB_RANK_LAYOUT"] = layout
+    out = _run(world, port, env)
+    assert out.count("slices_ok=True") == 10, out
+    if layout:
+        assert "layout=cyclic" not in out, out
 
 
 def test_shard_bounds():

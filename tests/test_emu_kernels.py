@@ -93,63 +93,12 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
     assert st["group_sort_records"] > st["group_big_records"] > 0, st
 
 
-def test_emu_peer_rank_kernels_both_layouts(emu_lib):
-    """The peer-to-peer gather / scatter kernels of the multi-GPU rounds against a numpy model of both rank[]
-    layouts: the "peers" are P separate arrays of this process (the emulator's device memory is host memory)."""
-    import ctypes as C
-    from suffix_array_b200 import dist as sdist
-    L = sdist._bind(emu_lib)
-    rng = np.random.default_rng(5)
-    for n, P in ((1000, 3), (4097, 2), (70000, 8), (5, 4)):
-        for kind in ("block", "cyclic"):
-            lay = sdist.RankLayout(n, P, kind)
-
-            def owner_slot(q):
-                if kind == "cyclic":
-                    b = q >> lay.shift
-                    return b % P, ((b // P) << lay.shift) | (q & (lay.width - 1))
-                o = min(q // lay.width, P - 1)
-                return o, q - o * lay.width
-
-            peers = [np.full(lay.local_len, 0xDEADBEEF, dtype=np.uint32) for _ in range(P)]
-            ptrs = np.array([p.ctypes.data for p in peers], dtype=np.uint64)
-            # every position 0..n lands in exactly one slot, inside the local arrays
-            seen = set()
-            for q in range(n + 1):
-                o, s = owner_slot(q)
-                assert 0 <= o < P and 0 <= s < lay.local_len and (o, s) not in seen
-                seen.add((o, s))
-            idx = rng.permutation(n + 1).astype(np.uint32)
-            val = rng.integers(0, 2 ** 32, n + 1, dtype=np.uint64).astype(np.uint32)
-            skip = rng.random(n + 1) < 0.1
-            idx_in = np.where(skip, np.uint32(0xFFFFFFFF), idx).astype(np.uint32)
-            rc = L.sab200_dist_scatter_p2p(idx_in.ctypes.data, val.ctypes.data, n + 1, lay.width, P, lay.shift,
-                                           ptrs.ctypes.data_as(C.c_void_p), 0)
-            assert rc == 0
-            model = np.full(n + 1, 0xDEADBEEF, dtype=np.uint32)
-            model[idx[~skip]] = val[~skip]
-            for q in range(n + 1):
-                o, s = owner_slot(q)
-                assert peers[o][s] == model[q], (n, P, kind, q)
-            h = 3
-            m = max(1, n - h)
-            pos = rng.integers(0, n + 1 - h, m, dtype=np.uint64).astype(np.uint32)
-            r1 = rng.integers(0, 2 ** 32, m, dtype=np.uint64).astype(np.uint32)
-            key64 = np.zeros(m, dtype=np.uint64)
-            rc = L.sab200_dist_gather_p2p(r1.ctypes.data, pos.ctypes.data, m, h, lay.width, P, lay.shift,
-                                          ptrs.ctypes.data_as(C.c_void_p), key64.ctypes.data, 0)
-            assert rc == 0
-            exp = (r1.astype(np.uint64) << np.uint64(32)) | model[pos.astype(np.int64) + h].astype(np.uint64)
-            assert np.array_equal(key64, exp), (n, P, kind)
-
-
 def test_emu_radix_sort_direct(emu_lib):
-    """The LSD radix sort on its own (through sab200_dist_sort_pairs): stable order of (key, payload) pairs
+    """The LSD radix sort on its own (through sab200_sort_pairs_device): stable order of (key, payload) pairs
     against numpy for sizes around the tile (4096) and look-back group (8 tiles) limits and for skewed,
     constant and wide digits -- the two-level look-back sees complete, partial and single groups."""
     import ctypes as C
-    from suffix_array_b200 import dist as sdist
-    L = sdist._bind(emu_lib)
+    L = emu_lib
     rng = np.random.default_rng(123)
     cases = []
     for n in (1, 31, 4095, 4096, 4097, 8 * 4096, 8 * 4096 + 1, 9 * 4096 - 1, 70000, 17 * 4096):
@@ -164,7 +113,7 @@ def test_emu_radix_sort_direct(emu_lib):
         vals = rng.permutation(n).astype(np.uint32)
         k0, v0 = keys.copy(), vals.copy()
         k1, v1 = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
-        which = L.sab200_dist_sort_pairs(k0.ctypes.data, k1.ctypes.data, v0.ctypes.data, v1.ctypes.data, n, bits, 0)
+        which = L.sab200_sort_pairs_device(k0.ctypes.data, k1.ctypes.data, v0.ctypes.data, v1.ctypes.data, n, bits, 0)
         assert which in (0, 1), which
         ks, vs = (k0, v0) if which == 0 else (k1, v1)
         order = np.argsort(keys, kind="stable")
@@ -184,7 +133,8 @@ def test_argument_errors(emu_lib):
     assert b"MAX_LENGTH" in L.sab200_last_error() or L.sab200_last_error()
     assert L.sab200_saca(txt.ctypes.data, 4, None, 1) == -1
     assert L.sab200_saca(None, 4, buf.ctypes.data, 1) == -1
-    assert L.sab200_saca(txt.ctypes.data, 4, buf.ctypes.data, 2) == -1      # multi-GPU = one process per GPU (sab200_dist.h)
+    assert L.sab200_saca(txt.ctypes.data, 4, buf.ctypes.data, 2) == -1      # more GPUs than visible (the emulator has one)
+    assert L.sab200_saca(txt.ctypes.data, 4, buf.ctypes.data, 17) == -1
     assert L.sab200_enable_buckets(txt.ctypes.data, too_long, buf.ctypes.data) == -1
     assert L.sab200_check(txt.ctypes.data, too_long, buf.ctypes.data, 5) == -1
     assert not L.sab200_index_create(txt.ctypes.data, 4, None, 5, None, 1)
@@ -195,27 +145,6 @@ def test_argument_errors(emu_lib):
     sa0 = np.full(1, 7, dtype=np.uint32)
     assert L.sab200_saca(None, 0, sa0.ctypes.data, 1) == 0 and sa0[0] == 0
     assert L.sab200_check(None, 0, sa0.ctypes.data, 1) == 1
-
-
-def _random_text(rng):
-    """Texts with structure: runs, repeats with mutations, mixtures of unique and repetitive regions."""
-    from suffix_array_b200 import gen
-    kind = int(rng.integers(0, 6))
-    n = int(rng.integers(1, 40000))
-    if kind == 0:
-        return rng.integers(0, int(rng.integers(1, 6)), n, dtype=np.uint8)
-    if kind == 1:
-        return gen.dna_like(n)
-    if kind == 2:
-        return gen.repetitive(n, block=int(rng.integers(8, 3000)), mut_rate=float(rng.choice([0, 1e-3, 1e-2, 1e-1])))
-    if kind == 3:
-        return gen.mixed_range(max(n, 64), 0, max(n, 64))
-    if kind == 4:
-        a = rng.integers(0, 256, n // 2 + 1, dtype=np.uint8)
-        b = np.tile(rng.integers(97, 101, int(rng.integers(3, 90)), dtype=np.uint8), n // 50 + 2)
-        return np.concatenate([a, b, a[:n // 5]])
-    base = gen.repetitive(max(n, 100), block=int(rng.integers(50, 1500)), mut_rate=float(rng.choice([1e-3, 1e-2])))
-    return np.concatenate([base, gen.dna_like(max(n // 3, 10)), base[:n // 2]])
 
 
 @pytest.mark.parametrize("build", ["emu", "emu-prod"])
@@ -234,4 +163,4 @@ def test_emu_randomized_construction(build, emu_lib, oracle, monkeypatch):
     monkeypatch.setattr(_lib, "_lib", lib)
     rng = np.random.default_rng(2026)
     for _ in range(16):
-        pc.check_construction(oracle, _random_text(rng))
+        pc.check_construction(oracle, pc.random_text(rng))
