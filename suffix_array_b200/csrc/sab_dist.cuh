@@ -75,6 +75,24 @@ __global__ void dist_place_keys_kernel(const u32* __restrict__ r1, const u32* __
     }
 }
 
+// SA entries that became final on a GPU that does not hold their position (rebalanced lists): sa[pos] = idx
+__global__ void dist_store_sa_kernel(const u32* __restrict__ pos, const u32* __restrict__ idx, u64 n, u32 sa_off,
+                                     u32* __restrict__ sa_local) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sa_local[pos[i] - sa_off] = idx[i];
+}
+// For every cut c = cuts[j] inside the rank-sorted list r1[0..m) (j = blockIdx.x / blocks_per_cut): the smallest
+// p in [c + woff, c + woff + window) with r1[p] != r1[c-1] (atomicMin into out[j], pre-set to ~0).
+__global__ void find_boundary_kernel(const u32* __restrict__ r1, u64 m, const u64* __restrict__ cuts, u32 blocks_per_cut, u64 woff,
+                                     u64 window, unsigned long long* __restrict__ out) {
+    const u32 j = blockIdx.x / blocks_per_cut;
+    const u64 c = cuts[j];
+    if (c == 0 || c >= m) return;
+    const u64 t = (u64)(blockIdx.x % blocks_per_cut) * blockDim.x + threadIdx.x;
+    const u64 p = c + woff + t;
+    if (t < window && p < m && r1[p] != r1[c - 1]) atomicMin(&out[j], (unsigned long long)p);
+}
+
 // ---- lazy inverse suffix array, distributed (see the file header, step 6)
 __global__ void __launch_bounds__(256)
 dist_lazy_collect_kernel(const u32* __restrict__ q, const u32* __restrict__ ans, u64 count, u32 h, u64 shard_lo,
@@ -505,6 +523,15 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
 
         // ---- 8. doubling rounds
         SortBuffers<u64> rb;
+        u32 slice_start[SAB_MAX_RANKS];  // first SA position of every slice
+        {
+            u64 run = 1;
+            for (int r = 0; r < SAB_MAX_RANKS; ++r) {
+                slice_start[r] = r < P ? (u32)run : 0xffffffffu;
+                if (r < P)
+                    for (int s = 0; s < P; ++s) run += mat[(size_t)s * P + r];
+            }
+        }
         u64 key_cap;
         if (lazy) {
             rb.k[0] = freeK;
@@ -520,6 +547,84 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
         rb.cur = 0;
         const u64 val_cap = R + 8;
         u32* sa_shifted = sa_local - (size_t)sa_off;  // ranks are global SA positions
+        // ---- 7b. even out the active lists.  The slices hold equal numbers of SUFFIXES, not of active ones (on the
+        // mixed text the English-like key ranges hold nearly all of them) and a round costs what its longest list
+        // costs.  The lists are globally sorted by rank and groups never straddle GPUs: cut points move to group
+        // boundaries and contiguous chunks are shipped, which keeps both properties.  A suffix that becomes unique
+        // on a GPU that does not hold its SA position is then routed to the slice owner (step f of a round).
+        ph.mark(7);
+        if (P > 1) {
+            u64 mine[SAB_MAX_RANKS], mm[SAB_MAX_RANKS * SAB_MAX_RANKS];
+            for (int d = 0; d < P; ++d) mine[d] = m;
+            SAB_TRY(sab_comm_count_matrix(cm, st, mine, mm));  // mm[s*P + *] = list length of rank s
+            u64 M = 0, mx = 0, off = 0;
+            for (int s = 0; s < P; ++s) {
+                const u64 v = mm[(size_t)s * P];
+                M += v;
+                if (v > mx) mx = v;
+                if (s < g) off += v;
+            }
+            const u64 rebal_min = (u64)sab_env_int("SAB_REBALANCE_MIN", 1 << 20);
+            if (M >= rebal_min * (u64)P && (double)mx * P > 1.1 * (double)M) {
+                const u64 Q = div_up64(M, (u64)P);
+                u64* h = (u64*)(c->h_small + 1024);
+                u64 cuts[SAB_MAX_RANKS], found[SAB_MAX_RANKS];
+                for (int j = 1; j < P; ++j) {
+                    const u64 want = (u64)j * Q;
+                    cuts[j - 1] = want <= off ? 0 : (want - off >= m ? m : want - off);
+                    found[j - 1] = (cuts[j - 1] == 0 || cuts[j - 1] >= m) ? cuts[j - 1] : ~0ull;
+                }
+                u64* d_cuts = c->d_ghist;             // [P-1] cuts, then [P-1] results
+                unsigned long long* d_found = (unsigned long long*)(c->d_ghist + SAB_MAX_RANKS);
+                memcpy(h, cuts, sizeof(u64) * (P - 1));
+                SAB_CUDA_TRY(cudaMemcpyAsync(d_cuts, h, sizeof(u64) * (P - 1), cudaMemcpyHostToDevice, st));
+                u64 woff = 0, window = 1 << 16;
+                for (;;) {
+                    bool open = false;
+                    for (int j = 0; j < P - 1; ++j) open = open || found[j] == ~0ull;
+                    if (!open) break;
+                    SAB_CUDA_TRY(cudaMemsetAsync(d_found, 0xff, sizeof(u64) * (P - 1), st));
+                    const u32 bpc = (u32)div_up64(window, 256);
+                    SAB_LAUNCH(find_boundary_kernel, bpc * (unsigned)(P - 1), 256, 0, st, (const u32*)r1buf, m, (const u64*)d_cuts, bpc, woff,
+                               window, d_found);
+                    SAB_LAUNCH_CHECK();
+                    SAB_CUDA_TRY(cudaMemcpyAsync(h + 32, d_found, sizeof(u64) * (P - 1), cudaMemcpyDeviceToHost, st));
+                    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+                    for (int j = 0; j < P - 1; ++j) {
+                        if (found[j] != ~0ull) continue;
+                        if (h[32 + j] != ~0ull) found[j] = h[32 + j];
+                        else if (cuts[j] + woff + window >= m) found[j] = m;  // the group runs to the end of the list
+                    }
+                    woff += window;
+                    window *= 8;
+                }
+                u64 bounds[SAB_MAX_RANKS + 1], sendc[SAB_MAX_RANKS];
+                bounds[0] = 0;
+                for (int j = 1; j < P; ++j) bounds[j] = found[j - 1] > bounds[j - 1] ? found[j - 1] : bounds[j - 1];
+                bounds[P] = m;
+                for (int j = 0; j < P; ++j) sendc[j] = bounds[j + 1] - bounds[j];
+                A2APlan pb;
+                SAB_TRY(sab_comm_plan(cm, st, sendc, &pb, nullptr));
+                const u64 cap = key_cap < val_cap ? key_cap : val_cap;
+                u64 bad = pb.rtotal + 64 > cap ? 1 : 0;
+                SAB_TRY(sab_comm_sum_u64(cm, st, &bad, 1));
+                if (bad == 0) {
+                    const size_t mark = A.hi;
+                    u32* t1 = A.top<u32>(pb.rtotal + 8);
+                    u32* t2 = A.top<u32>(pb.rtotal + 8);
+                    SAB_ARENA_CHECK(A);
+                    SAB_TRY(sab_comm_exchange(cm, st, pb, r1buf, t1, sizeof(u32)));
+                    SAB_TRY(sab_comm_exchange(cm, st, pb, rb.v[rb.cur], t2, sizeof(u32)));
+                    m = pb.rtotal;
+                    if (m) {
+                        SAB_CUDA_TRY(cudaMemcpyAsync(r1buf, t1, m * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+                        SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur], t2, m * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+                    }
+                    A.hi = mark;
+                    rebalanced = true;
+                }
+            }
+        }
         const int rank_bits = sab_ceil_log2_u64(n + 2);
         bool group_sort_on = SAB_GROUP_SORT != 0;
         u64 h = (u64)k;
@@ -626,6 +731,8 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
             u64 kept = 0;
             u32* upd_idx = A.top<u32>(m + 8);
             u32* upd_r = A.top<u32>(m + 8);
+            u32* set_pos = rebalanced ? A.top<u32>(m + 8) : nullptr;
+            const u32* sorted_idx = nullptr;
             SAB_ARENA_CHECK(A);
             if (m) {
                 SortBuffers<u64> sb;
@@ -662,15 +769,64 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 TileState<RerankScan> ts = sab_tile_state<RerankScan>(c, tiles);
                 sab_prof_begin(c, 3);
                 SAB_LAUNCH(rerank_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, (const u64*)sb.k[sb.cur], (const u32*)sb.v[sb.cur], m,
-                           (u32*)nullptr, sa_shifted, r1buf, out_idx, upd_idx, upd_r, (u32*)nullptr, d_m, ts);
+                           (u32*)nullptr, sa_shifted, r1buf, out_idx, upd_idx, upd_r, set_pos, d_m, ts);
                 sab_prof_end(c);
                 SAB_LAUNCH_CHECK();
                 S.kernel_launches++;
                 SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
                 SAB_CUDA_TRY(cudaStreamSynchronize(st));
                 kept = c->h_small[0];
+                sorted_idx = sb.v[sb.cur];
+                if (rebalanced) {
+                    // f. new SA entries to the GPUs that hold their positions (before the buffer of the sorted
+                    // indices is reused for the next list)
+                    ph.mark(13);
+                    const size_t mark2 = A.hi;
+                    u32* kp = A.top<u32>(m + 8);
+                    u32* vp = A.top<u32>(m + 8);
+                    SAB_ARENA_CHECK(A);
+                    SliceDigit sld;
+                    for (int i = 0; i < SAB_MAX_RANKS; ++i) sld.start[i] = slice_start[i];
+                    sld.pmax = (u32)P - 1;
+                    u64 cnt_s[SAB_MAX_RANKS];
+                    SAB_TRY((sab_count_and_base<u32, SliceDigit>(c, set_pos, m, sld, P, cnt_s)));
+                    A2APlan ps;
+                    SAB_TRY(sab_comm_plan(cm, st, cnt_s, &ps, nullptr));
+                    SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(m, PTILE)));
+                    SAB_TRY((sab_launch_pass_op<u32, false, SliceDigit>(c, set_pos, kp, sorted_idx, vp, m, sld, c->d_gbase)));
+                    u32* rp = A.top<u32>(ps.rtotal + 8);
+                    u32* ri = A.top<u32>(ps.rtotal + 8);
+                    SAB_ARENA_CHECK(A);
+                    SAB_TRY(sab_comm_exchange(cm, st, ps, kp, rp, sizeof(u32)));
+                    SAB_TRY(sab_comm_exchange(cm, st, ps, vp, ri, sizeof(u32)));
+                    if (ps.rtotal) {
+                        SAB_LAUNCH(dist_store_sa_kernel, (unsigned)div_up64(ps.rtotal, 256), 256, 0, st, (const u32*)rp, (const u32*)ri,
+                                   ps.rtotal, (u32)sa_off, sa_local);
+                        SAB_LAUNCH_CHECK();
+                        S.kernel_launches++;
+                    }
+                    A.hi = mark2;
+                }
                 if (sb.cur != 0 && kept > 0)
                     SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1], rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            } else if (rebalanced) {
+                // a rank with an empty list still takes part in the collectives of step f
+                ph.mark(13);
+                u64 cnt_s[SAB_MAX_RANKS] = {0};
+                A2APlan ps;
+                SAB_TRY(sab_comm_plan(cm, st, cnt_s, &ps, nullptr));
+                const size_t mark2 = A.hi;
+                u32* rp = A.top<u32>(ps.rtotal + 8);
+                u32* ri = A.top<u32>(ps.rtotal + 8);
+                SAB_ARENA_CHECK(A);
+                SAB_TRY(sab_comm_exchange(cm, st, ps, rp, rp, sizeof(u32)));
+                SAB_TRY(sab_comm_exchange(cm, st, ps, ri, ri, sizeof(u32)));
+                if (ps.rtotal) {
+                    SAB_LAUNCH(dist_store_sa_kernel, (unsigned)div_up64(ps.rtotal, 256), 256, 0, st, (const u32*)rp, (const u32*)ri,
+                               ps.rtotal, (u32)sa_off, sa_local);
+                    SAB_LAUNCH_CHECK();
+                }
+                A.hi = mark2;
             }
             // e. changed ranks to their owners
             ph.mark(12);

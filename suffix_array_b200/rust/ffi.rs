@@ -22,6 +22,7 @@ extern "C" {
     pub fn sab200_pack_bound(sa_len: u64) -> u64;
     pub fn sab200_pack(sa: *const u32, sa_len: u64, out: *mut u8, out_cap: u64, out_len: *mut u64) -> i32;
     pub fn sab200_unpack(bytes: *const u8, nbytes: u64, sa: *mut u32, sa_cap: u64, sa_len: *mut u64) -> i32;
+    pub fn sab200_device_count() -> i32;
     pub fn sab200_last_error() -> *const c_char;
     pub fn sab200_shutdown();
 }

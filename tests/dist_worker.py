@@ -54,7 +54,8 @@ def main():
              np.frombuffer(b"mississippi" * 7, dtype=np.uint8), np.full(3000, 97, dtype=np.uint8),
              np.frombuffer(b"\x00\xff" * 900 + b"\x00", dtype=np.uint8), gen.dna_like(20000), gen.uniform_bytes(9000),
              gen.repetitive(12000, block=257, mut_rate=2e-3), gen.mixed(7000),
-             rng.integers(0, 3, 5001, dtype=np.uint8), planted(rng, 40000, 256, 1500, 4), planted(rng, 30000, 4, 900, 3)]
+             rng.integers(0, 3, 5001, dtype=np.uint8), planted(rng, 40000, 256, 1500, 4), planted(rng, 30000, 4, 900, 3),
+             np.concatenate([gen.uniform_bytes(26000), gen.english_like(6000)])]
     fuzz = int(os.environ.get("SAB_DIST_FUZZ", "0"))
     if fuzz:  # fixed-seed randomized texts (runs, repeats with mutations, mixtures): same list on every rank
         from tests import parity_cases as pc

@@ -27,14 +27,17 @@ def test_dist_construction_gloo(emu_lib, world, port, lib):
     array, block-cyclic rank[] ownership); the build with the production cost-model constant leaves few
     (lazy inverse suffix array: EMPTY look-ups resolved through the keys)."""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "suffix_array_b200", "csrc"), "emu-prod"], stdout=subprocess.DEVNULL)
-    out = _run(world, port, {"SAB_EMU_LIB": lib})
-    assert out.count("slices_ok=True") == 13, out
+    out = _run(world, port, {"SAB_EMU_LIB": lib, "SAB_REBALANCE_MIN": "0"})  # even out the active lists whenever they are uneven
+    assert out.count("slices_ok=True") == 14, out
     if lib.endswith("prod.so"):
         assert out.count("lazy=True") >= 2, out
         resolved = [int(l.split("resolved=")[1].split()[0]) for l in out.splitlines() if "lazy=True" in l]
         assert sum(1 for r in resolved if r > 0) >= 1, out
         deep = [int(l.split("rounds=")[1].split()[0]) for l in out.splitlines() if "lazy=True" in l]
         assert max(deep) >= 4, out  # look-ups and memoised ranks over several rounds
+        # evened-out lists (new SA entries routed to their slices), with and without the lazy inverse suffix array
+        assert any("rebalanced=True" in l and "lazy=True" in l and "rounds=1 " not in l for l in out.splitlines()), out
+        assert any("rebalanced=True" in l and "lazy=False" in l for l in out.splitlines()), out
     else:
         assert out.count("layout=cyclic") >= 5, out
 

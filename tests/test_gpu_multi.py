@@ -26,7 +26,7 @@ def test_dist_construction_nccl(gpu_lib, world, port, env):
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=dict(os.environ, SAB_DIST_BACKEND="nccl", **env), cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    expect = int(env.get("SAB_DIST_FUZZ", 0)) or 18
+    expect = int(env.get("SAB_DIST_FUZZ", 0)) or 19
     assert out.stdout.count("slices_ok=True") == expect, out.stdout
     if not env:
         assert "lazy=True" in out.stdout and "layout=cyclic" in out.stdout, out.stdout
