@@ -365,7 +365,7 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     if (count) {
         sab_prof_begin(c, 2);
         SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, avail, count,
-                   (const u16*)d_lut, base, k, sab_pow_u64(base, k - 1), keysA);
+                   (const u16*)d_lut, base, k, sab_pack_pow(base, k), keysA);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         S.kernel_launches++;
@@ -439,12 +439,13 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     u32* sa_local = A.bot<u32>(R + 8);
     u32* r1buf = A.bot<u32>(R + 8);
     SAB_ARENA_CHECK(A);
-    SAB_TRY(sab_radix_sort<u64>(c, buf, R, 0, key_bits, /*iota=*/false, &S.passes[0]));
+    bool sa_written = false;  // the last pass writes the sorted indices straight into the slice of sa[]
+    SAB_TRY(sab_radix_sort<u64>(c, buf, R, 0, key_bits, /*iota=*/false, &S.passes[0], sa_local, &sa_written));
 
     // ---- 6. ranks, slice of sa[], active list, bucket directory over the slice's keys
     ph.mark(5);
     const u64* sortedK = buf.k[buf.cur];
-    const u32* sortedI = buf.v[buf.cur];
+    const u32* sortedI = sa_written ? sa_local : buf.v[buf.cur];
     u64* freeK = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
     u32* rank_seq = (u32*)freeK;
@@ -470,7 +471,7 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
         TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
         sab_prof_begin(c, 3);
         SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, R, (u32)sa_off, (u32*)nullptr, rank_seq,
-                   sa_local, r1buf, act_idx, d_m, dir_shifted, dir_shift, ts);
+                   sa_written ? (u32*)nullptr : sa_local, r1buf, act_idx, d_m, dir_shifted, dir_shift, ts);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         S.kernel_launches++;

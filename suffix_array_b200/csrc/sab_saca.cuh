@@ -104,8 +104,21 @@ __device__ __forceinline__ u64 pack_key_at(const u8* __restrict__ text, u64 n, c
 // when the buffer is a shard + halo).  Each thread owns SAB_PACK_ITEMS consecutive positions: the first
 // key costs k multiply-adds, each next one slides the window (drop the leading symbol, append one);
 // the keys leave through shared memory so that global stores are coalesced.
+struct PackPow {
+    u64 p[64];  // p[t] = radix^(k-1-t): weight of symbol t of a key
+};
+static inline PackPow sab_pack_pow(u32 radix, int k) {
+    PackPow w;
+    memset(&w, 0, sizeof(w));
+    u64 v = 1;
+    for (int t = k - 1; t >= 0; --t) {
+        w.p[t] = v;
+        v *= radix;
+    }
+    return w;
+}
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
-pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k, u64 top,
+pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k, PackPow pw,
                  u64* __restrict__ keys) {
     SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
@@ -120,8 +133,11 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
     }
     __syncthreads();
     const int o0 = threadIdx.x * SAB_PACK_ITEMS;
+    const u64 top = pw.p[0];
+    // first key: independent multiplies by the symbol weights (a Horner chain would serialise k 64-bit multiplies)
     u64 key = 0;
-    for (int t = 0; t < k; ++t) key = key * radix + (u64)s_code[o0 + t];
+#pragma unroll 4
+    for (int t = 0; t < k; ++t) key += (u64)s_code[o0 + t] * pw.p[t];
 #pragma unroll
     for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
         s_lo[SAB_PAD(o0 + j)] = (u32)key;
@@ -372,21 +388,22 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     memcpy(c->h_small + 384, lut, sizeof(lut));  // pinned staging: the async copy must not read the stack later
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
 
-    const u64 top = sab_pow_u64(base, k - 1);
     // 2. packed keys
     SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
-               (const u16*)d_lut, base, k, top, buf.k[0]);
+               (const u16*)d_lut, base, k, sab_pack_pow(base, k), buf.k[0]);
     sab_prof_end(c);
     SAB_LAUNCH_CHECK();
     S.kernel_launches++;
 
     // 3. sort (key, i); the payload of the first pass is generated, not read
-    SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, key_bits, /*iota=*/true, &S.passes[0]));
+    // (the last pass writes the sorted indices straight into sa[1..]: they need no copy afterwards)
+    bool sa_written = false;
+    SAB_TRY(sab_radix_sort<u64>(c, buf, n, 0, key_bits, /*iota=*/true, &S.passes[0], d_sa + 1, &sa_written));
 
     // 4. ranks, SA skeleton, active list, bucket directory over the sorted keys
     u32* d_m = c->d_counters;
     const u64* sortedK = buf.k[buf.cur];
-    const u32* sortedI = buf.v[buf.cur];
+    const u32* sortedI = sa_written ? d_sa + 1 : buf.v[buf.cur];
     u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
     int dir_bits = sab_ceil_log2_u64(n) - 4;
@@ -405,7 +422,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
         TileState<RankScan> ts = sab_tile_state<RankScan>(c, tiles);
         sab_prof_begin(c, 3);
         SAB_LAUNCH(init_ranks_kernel, (unsigned)tiles, SAB_SCAN_THREADS, 0, st, sortedK, sortedI, n, 1u, rank,
-                   (u32*)nullptr, d_sa + 1, r1buf, act_idx, d_m, dir, dir_shift, ts);
+                   (u32*)nullptr, sa_written ? (u32*)nullptr : d_sa + 1, r1buf, act_idx, d_m, dir, dir_shift, ts);
         sab_prof_end(c);
         SAB_LAUNCH_CHECK();
         S.kernel_launches++;

@@ -87,7 +87,9 @@ struct RankScanOp {
 
 // K, I: records sorted by key.  The rank of record j is r = rank_base + (index of the head of j's group)
 // (rank_base = SA position of record 0: 1 on a single GPU, the slice offset on a multi-GPU rank).
-//   sa_out[j] = I[j]                                  (coalesced copy)
+//   sa_out[j] = I[j]                                  (coalesced copy; sa_out == null: I already IS the slice of the
+//                                                      suffix array -- the last radix pass wrote it there -- and
+//                                                      only the indices of active records are loaded)
 //   records of groups larger than one -> (act_r1, act_idx)
 //   rank != null:     rank[I[j]] = r for those active records only (lazy ISA)
 //   rank_seq != null: rank_seq[j] = r for every record (multi-GPU: ranks travel to the owner of I[j])
@@ -103,13 +105,15 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
     ChunkKeys ck;
     ck.load(K, wbase, n);
     u32 idx[SAB_SCAN_ITEMS];
+    if (sa_out) {
 #pragma unroll
-    for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
-        const u64 j = wbase + (u64)k * 32 + lane;
-        idx[k] = 0;
-        if (j < n) {
-            idx[k] = I[j];
-            sa_out[j] = idx[k];
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) {
+            const u64 j = wbase + (u64)k * 32 + lane;
+            idx[k] = 0;
+            if (j < n) {
+                idx[k] = I[j];
+                sa_out[j] = idx[k];
+            }
         }
     }
     u32 hb[SAB_SCAN_ITEMS], ab[SAB_SCAN_ITEMS];
@@ -130,6 +134,10 @@ init_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, u64 n, u
         if (dir && head && (j == 0 || (ck.key[k] >> dir_shift) != (pk >> dir_shift))) dir[ck.key[k] >> dir_shift] = (u32)j;
         if (hb[k]) mine.head = (u32)row + high_bit(hb[k]);
         mine.cnt += (u32)__popc(ab[k]);
+    }
+    if (!sa_out) {  // requested before the look-back so that their latency hides behind it
+#pragma unroll
+        for (int k = 0; k < SAB_SCAN_ITEMS; ++k) idx[k] = ((ab[k] >> lane) & 1u) ? I[wbase + (u64)k * 32 + lane] : 0u;
     }
     RankScan ident;
     ident.head = 0;

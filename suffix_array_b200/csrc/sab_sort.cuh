@@ -73,10 +73,13 @@ static int sab_launch_pass(SabContext* c, const KeyT* kin, KeyT* kout, const u32
 // `iota` is set the incoming payload is ignored and taken to be 0..n-1.  On return buf.cur names
 // the buffers holding the result.  *passes_out receives the number of passes actually executed
 // (digit places where all keys agree are skipped).  Synchronises the stream once (skip flags).
+// final_v (optional): the LAST executed pass writes its payload there instead of into the double buffer (the
+// suffix array itself: the sorted indices need no copy afterwards); *final_used tells whether a pass did.
 template <typename KeyT>
 static int sab_radix_sort(SabContext* c, SortBuffers<KeyT>& buf, u64 n, int begin_bit, int end_bit, bool iota,
-                          u32* passes_out) {
+                          u32* passes_out, u32* final_v = nullptr, bool* final_used = nullptr) {
     if (passes_out) *passes_out = 0;
+    if (final_used) *final_used = false;
     if (n == 0) return SAB_OK;
     const int npass = (end_bit - begin_bit + SAB_RADIX_BITS - 1) / SAB_RADIX_BITS;
     if (npass < 0 || npass > SAB_MAX_PASSES) {
@@ -105,18 +108,25 @@ static int sab_radix_sort(SabContext* c, SortBuffers<KeyT>& buf, u64 n, int begi
         SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
         u32 skip[SAB_MAX_PASSES];
         memcpy(skip, c->h_small, sizeof(skip));
+        int last = -1;
+        for (int p = 0; p < npass; ++p)
+            if (!skip[p]) last = p;
+        const u32* vsrc = buf.v[buf.cur];
         for (int p = 0; p < npass; ++p) {
             if (skip[p]) continue;
             const int shift = begin_bit + p * SAB_RADIX_BITS;
             const int in = buf.cur, out = buf.cur ^ 1;
+            u32* vdst = (p == last && final_v) ? final_v : buf.v[out];
+            if (p == last && final_v && final_used) *final_used = true;
             if (!payload_ready) {
-                SAB_TRY((sab_launch_pass<KeyT, true>(c, buf.k[in], buf.k[out], nullptr, buf.v[out], n, shift,
+                SAB_TRY((sab_launch_pass<KeyT, true>(c, buf.k[in], buf.k[out], nullptr, vdst, n, shift,
                                                      c->d_gbase + p * SAB_RADIX_BINS)));
                 payload_ready = true;
             } else {
-                SAB_TRY((sab_launch_pass<KeyT, false>(c, buf.k[in], buf.k[out], buf.v[in], buf.v[out], n, shift,
+                SAB_TRY((sab_launch_pass<KeyT, false>(c, buf.k[in], buf.k[out], vsrc, vdst, n, shift,
                                                       c->d_gbase + p * SAB_RADIX_BINS)));
             }
+            vsrc = vdst;
             buf.cur = out;
             if (passes_out) *passes_out += 1;
         }
