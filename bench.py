@@ -557,11 +557,15 @@ def dist_case(L, _lib, torch, dist, gloo, comm, rank, local_rank, world, workloa
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     lib_ms = 0.0
+    host = {"wall_ms": 0.0, "host_setup_ms": 0.0, "host_finish_ms": 0.0}
     e0.record()
     for _ in range(steps):
         comm.saca(d_shard, n)       # blocks until this rank's library stream has drained
         launches += _lib.last_stats()["kernel_launches"]
-        lib_ms += comm.stats()["total_ms"]
+        cs = comm.stats()
+        lib_ms += cs["total_ms"]
+        for k_ in host:
+            host[k_] += cs[k_] / steps
     e1.record()
     barrier()
     dev_ms = allred(e0.elapsed_time(e1) / steps, dist.ReduceOp.MAX)
@@ -603,7 +607,8 @@ def dist_case(L, _lib, torch, dist, gloo, comm, rank, local_rank, world, workloa
            "rounds": st["rounds"], "active": st["active"], "lazy_isa": bool(st["lazy_isa"]),
            "rank_layout": "block-cyclic" if st["rank_layout"] else "block", "collectives_per_step": st["collectives"],
            "all_to_all_bytes_per_step": int(a2a), "largest_slice": int(max_slice), "phase_ms_rank0": phases,
-           "lib_stream_ms_rank0": round(lib_ms / steps, 3), "radix_pass_gbs_slowest_rank": round(achieved, 1),
+           "lib_stream_ms_rank0": round(lib_ms / steps, 3), "host_ms_rank0": {k_: round(v_, 3) for k_, v_ in host.items()},
+           "radix_pass_gbs_slowest_rank": round(achieved, 1),
            "radix_pass_share_max": round(pass_share, 3), "gpu_launches": int(tot_launches), "verification": ver,
            "verified": bool(ver and ver["verified"])}
     return rec, (text_full, sa_full)
@@ -659,7 +664,8 @@ def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
                            l2="inputs larger than L2 (no flush needed)", rounds=main_rec["rounds"], active=main_rec["active"],
                            lazy_isa=main_rec["lazy_isa"], rank_layout=main_rec["rank_layout"],
                            collectives_per_step=main_rec["collectives_per_step"], phase_ms_rank0=main_rec["phase_ms_rank0"],
-                           lib_stream_ms_rank0=main_rec["lib_stream_ms_rank0"], largest_slice=main_rec["largest_slice"],
+                           lib_stream_ms_rank0=main_rec["lib_stream_ms_rank0"], host_ms_rank0=main_rec["host_ms_rank0"],
+                           largest_slice=main_rec["largest_slice"],
                            all_to_all_bytes_per_step=main_rec["all_to_all_bytes_per_step"]),
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (LSD radix pass, slowest rank)",
                          "achieved": main_rec["radix_pass_gbs_slowest_rank"], "peak": peak, "unit": "GB/s",

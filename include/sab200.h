@@ -190,7 +190,10 @@ typedef struct sab200_dist_stats {
     uint64_t slice_len, sa_off, all_to_all_bytes, collectives, resolved_empty;
     uint64_t active[SAB200_MAX_ROUNDS]; /* active suffixes over all ranks entering round r (0 = after the initial sort) */
     double phase_ms[SAB200_PHASES];     /* CUDA events on the rank's stream */
-    double total_ms;
+    double total_ms;                    /* first to last event of the construction on the rank's stream */
+    double wall_ms;                     /* host clock around the whole call on this rank */
+    double host_setup_ms;               /* ... of which before the first event (context, arena) */
+    double host_finish_ms;              /* ... and after the last one (output copy excluded) */
 } sab200_dist_stats;
 /* Building block, exported for tests and tools: stable LSD radix sort of `count` (u64 key, u32 payload) records by
  * key bits [0, key_bits) over a double buffer of DEVICE memory on `device`.  Returns 0 / 1 = the buffer pair

@@ -70,6 +70,9 @@ class DistStats(C.Structure):
         ("active", C.c_uint64 * MAX_ROUNDS),
         ("phase_ms", C.c_double * PHASES),
         ("total_ms", C.c_double),
+        ("wall_ms", C.c_double),
+        ("host_setup_ms", C.c_double),
+        ("host_finish_ms", C.c_double),
     ]
 
     def as_dict(self):

@@ -32,6 +32,14 @@ struct sab200_comm {
     u64 bytes_sent = 0;
     u32 collectives = 0;
     sab200_dist_stats last;
+    // peers' device arenas mapped into this rank (fused key exchange): same process -> the pointer itself with peer
+    // access enabled, another process -> cudaIpcOpenMemHandle.  Re-validated on every call (see sab_peers_update).
+    struct Peer {
+        u64 pid = 0, dev = 0, ptr = 0, bytes = 0;
+        void* base = nullptr;
+        bool ipc = false;
+    } peers[SAB_MAX_RANKS];
+    bool peers_ok = false;
 };
 #define SAB_COMM_SCRATCH ((size_t)1 << 20)
 
@@ -112,6 +120,10 @@ static void sab_comm_free(sab200_comm* cm) {
     cudaSetDevice(cm->device);
 #ifndef SAB_EMU
     if (cm->kind == 0 && cm->nccl && cm->owns_nccl && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)cm->nccl);
+#endif
+#ifndef SAB_EMU
+    for (int i = 0; i < SAB_MAX_RANKS; ++i)
+        if (cm->peers[i].ipc && cm->peers[i].base) cudaIpcCloseMemHandle(cm->peers[i].base);
 #endif
     if (cm->d_small) cudaFree(cm->d_small);
     if (cm->h_small) cudaFreeHost(cm->h_small);
@@ -209,6 +221,18 @@ static int sab_comm_count_matrix(sab200_comm* cm, cudaStream_t st, const u64* mi
     SAB_CUDA_TRY(cudaMemcpyAsync(h + P, cm->d_small + P, (size_t)P * P * sizeof(u64), cudaMemcpyDeviceToHost, st));
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
     memcpy(mat, h + P, (size_t)P * P * sizeof(u64));
+    return SAB_OK;
+}
+
+// Every rank contributes a row of W u64 values already in cm->d_small[0..W) (device); rows[s*W + i] = value i of
+// rank s, on every rank's host.  One stream synchronisation.
+static int sab_comm_gather_rows(sab200_comm* cm, cudaStream_t st, int W, u64* rows) {
+    const int P = cm->P;
+    u64* d_all = cm->d_small + 64;
+    SAB_TRY(sab_comm_all_gather(cm, st, cm->d_small, d_all, (size_t)W * sizeof(u64)));
+    SAB_CUDA_TRY(cudaMemcpyAsync(cm->h_small + 64, d_all, (size_t)P * W * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(rows, cm->h_small + 64, (size_t)P * W * sizeof(u64));
     return SAB_OK;
 }
 

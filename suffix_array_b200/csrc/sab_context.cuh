@@ -66,6 +66,7 @@ struct SabContext {
     char* arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;
+    size_t arena_want_seen = 0;  // request the arena was last sized for (it may have been capped by the free memory)
     // profiling
     bool profiling = false;
     std::vector<SabEventPair> events;

@@ -20,6 +20,8 @@
 //
 // Every step is enqueued on the rank's library stream; the host only waits where it needs a count.
 #pragma once
+#include <unistd.h>
+
 #include <algorithm>
 #include <thread>
 
@@ -27,16 +29,40 @@
 #include "sab_saca.cuh"
 
 // ------------------------------------------------------------------ kernels
+// d_n != null: the record count lives on the device (the grid is sized for the bound n)
 template <typename KeyT, typename DigitOp>
-__global__ void __launch_bounds__(256) digit_count_kernel(const KeyT* __restrict__ keys, u64 n, DigitOp dop, u64* __restrict__ counts) {
+__global__ void __launch_bounds__(256) digit_count_kernel(const KeyT* __restrict__ keys, u64 n, const u32* __restrict__ d_n, DigitOp dop,
+                                                          u64* __restrict__ counts) {
     SAB_SHARED_ARRAY(u32, s_c, 256);
     s_c[threadIdx.x] = 0;
+    if (d_n) n = *d_n;
     __syncthreads();
     const u64 stride = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&s_c[dop(keys[i])], 1u);
     __syncthreads();
     const u32 c = s_c[threadIdx.x];
     if (c) atomicAdd((unsigned long long*)&counts[threadIdx.x], (unsigned long long)c);
+}
+
+// One block of 256 threads: gbase[] = exclusive prefix of the 256 bin counts (record offsets of the partition
+// pass), and the row this rank contributes to the count exchange: [P counts | nd device-side u32 extras].
+__global__ void __launch_bounds__(256)
+count_row_kernel(const u64* __restrict__ cnt, u64* __restrict__ gbase, int P, const u32* __restrict__ extra32, int nd,
+                 u64* __restrict__ row) {
+    SAB_SHARED_ARRAY(u64, s_v, 256);
+    const u32 t = threadIdx.x;
+    const u64 mine = cnt[t];
+    s_v[t] = mine;
+    __syncthreads();
+    for (u32 off = 1; off < 256; off <<= 1) {
+        const u64 v = t >= off ? s_v[t - off] : 0ull;
+        __syncthreads();
+        s_v[t] += v;
+        __syncthreads();
+    }
+    gbase[t] = s_v[t] - mine;
+    if ((int)t < P) row[t] = mine;
+    else if ((int)t < P + nd) row[t] = extra32[t - P];
 }
 
 __global__ void hist_widen_kernel(const u32* __restrict__ h32, u64* __restrict__ h64) { h64[threadIdx.x] = h32[threadIdx.x]; }
@@ -130,28 +156,40 @@ static inline unsigned sab_grid(SabContext* c, u64 n, u64 per_block, int waves) 
     return (unsigned)(g ? g : 1);
 }
 
-// counts of the first `bins` digits -> host; exclusive prefix over all 256 bins -> c->d_gbase[0..256)
+// Plans one variable all-to-all with a single host synchronisation:
+//   per-destination counts of keys[0..count) (count read from *d_count32 when given; `count` is then its bound)
+//   -> exclusive bases of all 256 bins in c->d_gbase (the partition pass of the same records follows)
+//   -> row [P counts | nd device u32 extras | nh host u64 extras] all-gathered: rows[s*W + i], W = P + nd + nh
+//   -> pl: what this rank sends to / receives from everybody.
 template <typename KeyT, typename DigitOp>
-static int sab_count_and_base(SabContext* c, const KeyT* d_keys, u64 count, DigitOp dop, int bins, u64* counts_host) {
+static int sab_plan_exchange(sab200_comm* cm, SabContext* c, const KeyT* d_keys, u64 count, const u32* d_count32, DigitOp dop,
+                             const u32* d_extra32, int nd, const u64* h_extra, int nh, A2APlan* pl, u64* rows) {
     cudaStream_t st = c->stream;
+    const int P = cm->P, W = P + nd + nh;
     u64* d_cnt = c->d_ghist;  // 256 x u64 scratch
     SAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 256 * sizeof(u64), st));
     if (count) {
-        SAB_LAUNCH((digit_count_kernel<KeyT, DigitOp>), sab_grid(c, count, 256 * 16, 8), 256, 0, st, d_keys, count, dop, d_cnt);
+        SAB_LAUNCH((digit_count_kernel<KeyT, DigitOp>), sab_grid(c, count, 256 * 16, 8), 256, 0, st, d_keys, count, d_count32, dop, d_cnt);
         SAB_LAUNCH_CHECK();
         c->stats.kernel_launches++;
     }
-    u64* h = (u64*)(c->h_small + 1024);  // 512 x u64 of the pinned scratch
-    SAB_CUDA_TRY(cudaMemcpyAsync(h, d_cnt, 256 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    SAB_CUDA_TRY(cudaStreamSynchronize(st));
-    for (int i = 0; i < bins; ++i) counts_host[i] = h[i];
-    u64 run = 0;
-    for (int i = 0; i < 256; ++i) {
-        const u64 v = h[i];
-        h[256 + i] = run;
-        run += v;
+    SAB_LAUNCH(count_row_kernel, 1, 256, 0, st, (const u64*)d_cnt, c->d_gbase, P, d_extra32, nd, cm->d_small);
+    SAB_LAUNCH_CHECK();
+    if (nh) {
+        u64* h = cm->h_small + 32;  // pinned staging (rows come back at h_small + 64)
+        for (int i = 0; i < nh; ++i) h[i] = h_extra[i];
+        SAB_CUDA_TRY(cudaMemcpyAsync(cm->d_small + P + nd, h, (size_t)nh * sizeof(u64), cudaMemcpyHostToDevice, st));
     }
-    SAB_CUDA_TRY(cudaMemcpyAsync(c->d_gbase, h + 256, 256 * sizeof(u64), cudaMemcpyHostToDevice, st));
+    u64 rows_[SAB_MAX_RANKS * 32];
+    u64* rr = rows ? rows : rows_;
+    SAB_TRY(sab_comm_gather_rows(cm, st, W, rr));
+    pl->stotal = pl->rtotal = 0;
+    for (int d = 0; d < P; ++d) {
+        pl->scount[d] = rr[(size_t)cm->rank * W + d];
+        pl->rcount[d] = rr[(size_t)d * W + cm->rank];
+        pl->stotal += pl->scount[d];
+        pl->rtotal += pl->rcount[d];
+    }
     return SAB_OK;
 }
 
@@ -241,12 +279,88 @@ static inline int sab_env_int(const char* name, int dflt) {
 static int sab_dist_reserve(SabContext* c, u64 B) {
     const size_t recs = (size_t)(B + B / 3) + ((size_t)1 << 20);
     size_t want = recs * 72 + ((size_t)256 << 20);
+    if (c->arena_bytes >= want || c->arena_want_seen == want) return SAB_OK;  // steady state: no driver call at all
+    c->arena_want_seen = want;
     size_t free_b = 0, total_b = 0;
     SAB_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t avail = (size_t)((double)(free_b + c->arena_bytes) * 0.94);
     if (want > avail) want = avail;
     return sab_arena_reserve(c, want);
 }
+
+#ifndef SAB_EMU
+// Keeps the peers' arenas mapped into this rank.  rows[s*W + P + {0,1,2,3}] = process id, device, arena address and
+// size of rank s (all-gathered with the key counts, so every rank sees the same table and takes the same
+// decisions).  A changed entry (first call, re-allocated arena) re-opens the mapping: cudaIpcOpenMemHandle for
+// another process, the pointer itself + cudaDeviceEnablePeerAccess inside one process.  Collective.
+static int sab_peers_update(sab200_comm* cm, SabContext* c, const u64* rows, int W) {
+    const int P = cm->P, g = cm->rank;
+    cudaStream_t st = c->stream;
+    bool changed = false;
+    for (int s = 0; s < P; ++s) {
+        const u64* r = rows + (size_t)s * W + P;
+        const sab200_comm::Peer& p = cm->peers[s];
+        if (p.pid != r[0] || p.dev != r[1] || p.ptr != r[2] || p.bytes != r[3]) changed = true;
+    }
+    if (!changed) return SAB_OK;  // peers_ok keeps its value
+    // 64-byte IPC handles of every arena
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    u64 fail = 0;
+    if (cudaIpcGetMemHandle(&mine, c->arena) != cudaSuccess) {
+        cudaGetLastError();
+        fail = 1;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(cm->h_small + 32, &mine, 64);
+    SAB_CUDA_TRY(cudaMemcpyAsync(cm->d_small, cm->h_small + 32, 64, cudaMemcpyHostToDevice, st));
+    SAB_TRY(sab_comm_all_gather(cm, st, cm->d_small, cm->d_small + 64, 64));
+    SAB_CUDA_TRY(cudaMemcpyAsync(cm->h_small + 64, cm->d_small + 64, (size_t)P * 64, cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    const u64 mypid = rows[(size_t)g * W + P];
+    for (int s = 0; s < P; ++s) {
+        const u64* r = rows + (size_t)s * W + P;
+        sab200_comm::Peer& p = cm->peers[s];
+        if (p.ipc && p.base) cudaIpcCloseMemHandle(p.base);
+        p.pid = r[0];
+        p.dev = r[1];
+        p.ptr = r[2];
+        p.bytes = r[3];
+        p.base = nullptr;
+        p.ipc = false;
+        if (s == g) {
+            p.base = c->arena;
+            continue;
+        }
+        if (p.pid == mypid) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->device, (int)p.dev) != cudaSuccess || !can) {
+                cudaGetLastError();
+                fail = 1;
+                continue;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess((int)p.dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fail = 1;
+            cudaGetLastError();
+            p.base = (void*)(uintptr_t)p.ptr;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)(cm->h_small + 64) + (size_t)s * 64, 64);
+            void* base = nullptr;
+            if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                fail = 1;
+                continue;
+            }
+            p.base = base;
+            p.ipc = true;
+        }
+    }
+    SAB_TRY(sab_comm_sum_u64(cm, st, &fail, 1));
+    cm->peers_ok = fail == 0;
+    return SAB_OK;
+}
+#endif
 
 struct DistRun {
     sab200_comm* cm;
@@ -257,8 +371,9 @@ struct DistRun {
     u32* rank_local;
     u64 lo;  // first text position of this rank
 
-    // rank[idx[t]] = val[t] on the GPU that owns text position idx[t]; records with idx = 0xFFFFFFFF are dropped
-    int send_ranks(const u32* idx, const u32* val, u64 cnt) {
+    // rank[idx[t]] = val[t] on the GPU that owns text position idx[t]; records with idx = 0xFFFFFFFF are dropped.
+    // d_extra32 / rows: nd device-side u32 values ride along with the count exchange (rows[s*(P+nd) + P + e]).
+    int send_ranks(const u32* idx, const u32* val, u64 cnt, const u32* d_extra32 = nullptr, int nd = 0, u64* rows = nullptr) {
         cudaStream_t st = c->stream;
         const size_t mark = A.hi;
         u32* kp = A.top<u32>(cnt + 8);
@@ -267,10 +382,8 @@ struct DistRun {
         OwnerDigit dop;
         dop.add = 0;
         dop.lay = lay;
-        u64 counts[SAB_MAX_RANKS];
-        SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, idx, cnt, dop, cm->P, counts)));
         A2APlan pl;
-        SAB_TRY(sab_comm_plan(cm, st, counts, &pl, nullptr));
+        SAB_TRY((sab_plan_exchange<u32, OwnerDigit>(cm, c, idx, cnt, nullptr, dop, d_extra32, nd, nullptr, 0, &pl, rows)));
         if (cnt) {
             SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(cnt, PassShape<u32>::THREADS * PassShape<u32>::ITEMS)));
             SAB_TRY((sab_launch_pass_op<u32, false, OwnerDigit>(c, idx, kp, val, vp, cnt, dop, c->d_gbase)));
@@ -401,31 +514,76 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     SplitterDigit sdop;
     sdop.np = P - 1;
     for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) sdop.s[i] = i < P - 1 ? splitters[i] : ~0ull;
-    u64 cnt_dst[SAB_MAX_RANKS];
-    SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, keysA, count, sdop, P, cnt_dst)));
     A2APlan pk;
     u64 mat[SAB_MAX_RANKS * SAB_MAX_RANKS];
-    SAB_TRY(sab_comm_plan(cm, st, cnt_dst, &pk, mat));
+    // the count exchange also carries what the peers need to address this rank's receive buffers directly
+    // (fused exchange, below): process, device, arena, offset of the key buffer inside it
+    const u64 k0_off = sab_align_up(A.lo, 256);
+    u64 extra[5] = {(u64)getpid(), (u64)c->device, (u64)(uintptr_t)c->arena, (u64)c->arena_bytes, k0_off};
+    constexpr int NX = 5;
+    u64 rows[SAB_MAX_RANKS * 32];
+    SAB_TRY((sab_plan_exchange<u64, SplitterDigit>(cm, c, keysA, count, nullptr, sdop, nullptr, 0, extra, NX, &pk, rows)));
+    const int W = P + NX;
+    for (int s = 0; s < P; ++s)
+        for (int d = 0; d < P; ++d) mat[(size_t)s * P + d] = rows[(size_t)s * W + d];
     const u64 R = pk.rtotal;
     u64 sa_off = 1;
     for (int r = 0; r < g; ++r)
         for (int s = 0; s < P; ++s) sa_off += mat[(size_t)s * P + r];
-    u64* partK = A.top<u64>(count + 8);
-    u32* partI = A.top<u32>(count + 8);
-    SAB_ARENA_CHECK(A);
     constexpr int PTILE = PassShape<u64>::THREADS * PassShape<u64>::ITEMS;
     SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64((count > R ? count : R) + 1, PTILE)));
     SAB_TRY(sab_ensure_scan(c, (size_t)div_up64(R + 4096, SAB_GSORT_TILE)));
-    if (count)
-        SAB_TRY((sab_launch_pass_op<u64, true, SplitterDigit>(c, keysA, partK, nullptr, partI, count, sdop, c->d_gbase, nullptr, (u32)lo)));
-
-    // ---- 4. key exchange
-    ph.mark(3);
     u64* K0 = A.bot<u64>(R + 8);
     u32* V0 = A.bot<u32>(R + 8);
     SAB_ARENA_CHECK(A);
-    SAB_TRY(sab_comm_exchange(cm, st, pk, partK, K0, sizeof(u64)));
-    SAB_TRY(sab_comm_exchange(cm, st, pk, partI, V0, sizeof(u32)));
+    bool fused = false;
+#ifndef SAB_EMU
+    if (P > 1 && cm->kind == 0 && sab_env_int("SAB_DIST_P2P", 1) != 0) {
+        SAB_TRY(sab_peers_update(cm, c, rows, W));
+        fused = cm->peers_ok;
+    }
+#endif
+    if (fused) {
+        // ---- 3+4 fused: the partition pass stores every record straight into its destination GPU's receive
+        // buffers over NVLink (rank s writes behind the records of the ranks before it): no staging copy, no
+        // all-to-all; the transfer overlaps the ranking tile by tile.  Every rank entered this call (alphabet
+        // all_reduce) before anybody stores, and the all_reduce below orders the stores before the local sort.
+        PeerOut po;
+        memset(&po, 0, sizeof(po));
+        u64* h = (u64*)(c->h_small + 1024);
+        for (int i = 0; i < 256; ++i) h[i] = 0;
+        for (int d = 0; d < P; ++d) {
+            u64 Rd = 0, before = 0;
+            for (int s = 0; s < P; ++s) {
+                Rd += mat[(size_t)s * P + d];
+                if (s < g) before += mat[(size_t)s * P + d];
+            }
+            const u64 koff = rows[(size_t)d * W + P + 4];
+            const u64 voff = sab_align_up(koff + (Rd + 8) * sizeof(u64), 256);
+            char* base = d == g ? c->arena : (char*)cm->peers[d].base;
+            po.k[d] = (u64)(uintptr_t)(base + koff);
+            po.v[d] = (u64)(uintptr_t)(base + voff);
+            h[d] = before;
+        }
+        SAB_CUDA_TRY(cudaMemcpyAsync(c->d_gbase, h, 256 * sizeof(u64), cudaMemcpyHostToDevice, st));
+        if (count)
+            SAB_TRY((sab_launch_pass_op<u64, true, SplitterDigit, true>(c, keysA, (u64*)nullptr, nullptr, (u32*)nullptr, count, sdop,
+                                                                       c->d_gbase, &po, (u32)lo)));
+        ph.mark(3);
+        SAB_TRY(sab_comm_all_reduce_u64(cm, st, cm->d_small, 1));  // barrier: all peers' stores have landed
+        for (int d = 0; d < P; ++d)
+            if (d != g) cm->bytes_sent += mat[(size_t)g * P + d] * 12;
+    } else {
+        u64* partK = A.top<u64>(count + 8);
+        u32* partI = A.top<u32>(count + 8);
+        SAB_ARENA_CHECK(A);
+        if (count)
+            SAB_TRY((sab_launch_pass_op<u64, true, SplitterDigit>(c, keysA, partK, nullptr, partI, count, sdop, c->d_gbase, nullptr, (u32)lo)));
+        // ---- 4. key exchange
+        ph.mark(3);
+        SAB_TRY(sab_comm_exchange(cm, st, pk, partK, K0, sizeof(u64)));
+        SAB_TRY(sab_comm_exchange(cm, st, pk, partI, V0, sizeof(u32)));
+    }
     A.hi = A0.hi;  // keysA, partK, partI are dead once the exchange has run (stream order)
 
     // ---- 5. local sort: this rank's slice of the suffix array
@@ -646,10 +804,8 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
             OwnerDigit odop;
             odop.add = (u32)h;
             odop.lay = lay;
-            u64 cnt_own[SAB_MAX_RANKS];
-            SAB_TRY((sab_count_and_base<u32, OwnerDigit>(c, cur_idx, m, odop, P, cnt_own)));
             A2APlan pr;
-            SAB_TRY(sab_comm_plan(cm, st, cnt_own, &pr, nullptr));
+            SAB_TRY((sab_plan_exchange<u32, OwnerDigit>(cm, c, cur_idx, m, nullptr, odop, nullptr, 0, nullptr, 0, &pr, nullptr)));
             if (m) {
                 SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(m, PTILE)));
                 SAB_TRY((sab_launch_pass_op<u32, true, OwnerDigit>(c, cur_idx, ipart, nullptr, ppart, m, odop, c->d_gbase)));
@@ -668,30 +824,28 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 S.kernel_launches++;
             }
             if (lazy) {
-                // b. requests that found EMPTY: key at the owner -> slice that holds the key -> rank back
+                // b. requests that found EMPTY: key at the owner -> slice that holds the key -> rank back.  Their
+                // number stays on the device until it comes back with the count exchange (one synchronisation).
                 ph.mark(9);
                 u64* keys_u = A.top<u64>(nq + 8);
                 u32* slot_u = A.top<u32>(nq + 8);
                 SAB_ARENA_CHECK(A);
-                u32* d_cnt = c->d_counters + 12;
-                SAB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(u32), st));
+                u32* d_nu = c->d_counters + 12;
+                SAB_CUDA_TRY(cudaMemsetAsync(d_nu, 0, sizeof(u32), st));
                 if (nq) {
                     SAB_LAUNCH(dist_lazy_collect_kernel, (unsigned)div_up64(nq, 256), 256, 0, st, (const u32*)q, (const u32*)ans, nq, (u32)h,
-                               lo, d_text, avail, (const u16*)d_lut, base, k, keys_u, slot_u, d_cnt);
+                               lo, d_text, avail, (const u16*)d_lut, base, k, keys_u, slot_u, d_nu);
                     SAB_LAUNCH_CHECK();
                     S.kernel_launches++;
                 }
-                SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 12, d_cnt, sizeof(u32), cudaMemcpyDeviceToHost, st));
-                SAB_CUDA_TRY(cudaStreamSynchronize(st));
-                const u64 nu = c->h_small[12];
+                A2APlan pu;
+                u64 rows_u[SAB_MAX_RANKS * 32];
+                SAB_TRY((sab_plan_exchange<u64, SplitterDigit>(cm, c, keys_u, nq, d_nu, sdop, d_nu, 1, nullptr, 0, &pu, rows_u)));
+                const u64 nu = rows_u[(size_t)g * (P + 1) + P];
                 ds->resolved_empty += nu;
                 u64* kp = A.top<u64>(nu + 8);
                 u32* sp = A.top<u32>(nu + 8);
                 SAB_ARENA_CHECK(A);
-                u64 cnt_u[SAB_MAX_RANKS];
-                SAB_TRY((sab_count_and_base<u64, SplitterDigit>(c, keys_u, nu, sdop, P, cnt_u)));
-                A2APlan pu;
-                SAB_TRY(sab_comm_plan(cm, st, cnt_u, &pu, nullptr));
                 if (nu) {
                     SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(nu, PTILE)));
                     SAB_TRY((sab_launch_pass_op<u64, false, SplitterDigit>(c, keys_u, kp, slot_u, sp, nu, sdop, c->d_gbase)));
@@ -729,12 +883,13 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
 
             // c. order inside the groups (as on one GPU: the list is still grouped by r1, ascending)
             ph.mark(10);
-            u64 kept = 0;
             u32* upd_idx = A.top<u32>(m + 8);
             u32* upd_r = A.top<u32>(m + 8);
             u32* set_pos = rebalanced ? A.top<u32>(m + 8) : nullptr;
             const u32* sorted_idx = nullptr;
+            int sorted_in = 0;  // which of the two index buffers holds the sorted list
             SAB_ARENA_CHECK(A);
+            SAB_CUDA_TRY(cudaMemsetAsync(d_m, 0, sizeof(u32), st));  // kept = 0 unless the re-rank says otherwise
             if (m) {
                 SortBuffers<u64> sb;
                 sb.k[0] = rb.k[rb.cur];
@@ -763,7 +918,8 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                     }
                 }
                 if (!sorted) SAB_TRY(sab_radix_sort<u64>(c, sb, m, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
-                // d. re-rank; newly unique suffixes go to sa[], changed ranks are collected for their owners
+                // d. re-rank; newly unique suffixes go to sa[], changed ranks are collected for their owners; the
+                // number of survivors stays on the device and comes back with the count exchange of step e
                 ph.mark(11);
                 u32* out_idx = (sb.cur == 0) ? rb.v[rb.cur ^ 1] : rb.v[rb.cur];
                 const u64 tiles = div_up64(m, SAB_SCAN_TILE);
@@ -774,70 +930,51 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 sab_prof_end(c);
                 SAB_LAUNCH_CHECK();
                 S.kernel_launches++;
-                SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
-                SAB_CUDA_TRY(cudaStreamSynchronize(st));
-                kept = c->h_small[0];
                 sorted_idx = sb.v[sb.cur];
-                if (rebalanced) {
-                    // f. new SA entries to the GPUs that hold their positions (before the buffer of the sorted
-                    // indices is reused for the next list)
-                    ph.mark(13);
-                    const size_t mark2 = A.hi;
-                    u32* kp = A.top<u32>(m + 8);
-                    u32* vp = A.top<u32>(m + 8);
-                    SAB_ARENA_CHECK(A);
-                    SliceDigit sld;
-                    for (int i = 0; i < SAB_MAX_RANKS; ++i) sld.start[i] = slice_start[i];
-                    sld.pmax = (u32)P - 1;
-                    u64 cnt_s[SAB_MAX_RANKS];
-                    SAB_TRY((sab_count_and_base<u32, SliceDigit>(c, set_pos, m, sld, P, cnt_s)));
-                    A2APlan ps;
-                    SAB_TRY(sab_comm_plan(cm, st, cnt_s, &ps, nullptr));
+                sorted_in = sb.cur;
+            }
+            if (rebalanced) {
+                // f. new SA entries to the GPUs that hold their positions (before the buffer of the sorted indices
+                // is reused for the next list); a rank with an empty list still takes part in the exchange
+                ph.mark(13);
+                const size_t mark2 = A.hi;
+                u32* kp = A.top<u32>(m + 8);
+                u32* vp = A.top<u32>(m + 8);
+                SAB_ARENA_CHECK(A);
+                SliceDigit sld;
+                for (int i = 0; i < SAB_MAX_RANKS; ++i) sld.start[i] = slice_start[i];
+                sld.pmax = (u32)P - 1;
+                A2APlan ps;
+                SAB_TRY((sab_plan_exchange<u32, SliceDigit>(cm, c, set_pos, m, nullptr, sld, nullptr, 0, nullptr, 0, &ps, nullptr)));
+                if (m) {
                     SAB_TRY(sab_ensure_lookback(c, (size_t)div_up64(m, PTILE)));
                     SAB_TRY((sab_launch_pass_op<u32, false, SliceDigit>(c, set_pos, kp, sorted_idx, vp, m, sld, c->d_gbase)));
-                    u32* rp = A.top<u32>(ps.rtotal + 8);
-                    u32* ri = A.top<u32>(ps.rtotal + 8);
-                    SAB_ARENA_CHECK(A);
-                    SAB_TRY(sab_comm_exchange(cm, st, ps, kp, rp, sizeof(u32)));
-                    SAB_TRY(sab_comm_exchange(cm, st, ps, vp, ri, sizeof(u32)));
-                    if (ps.rtotal) {
-                        SAB_LAUNCH(dist_store_sa_kernel, (unsigned)div_up64(ps.rtotal, 256), 256, 0, st, (const u32*)rp, (const u32*)ri,
-                                   ps.rtotal, (u32)sa_off, sa_local);
-                        SAB_LAUNCH_CHECK();
-                        S.kernel_launches++;
-                    }
-                    A.hi = mark2;
                 }
-                if (sb.cur != 0 && kept > 0)
-                    SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1], rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-            } else if (rebalanced) {
-                // a rank with an empty list still takes part in the collectives of step f
-                ph.mark(13);
-                u64 cnt_s[SAB_MAX_RANKS] = {0};
-                A2APlan ps;
-                SAB_TRY(sab_comm_plan(cm, st, cnt_s, &ps, nullptr));
-                const size_t mark2 = A.hi;
                 u32* rp = A.top<u32>(ps.rtotal + 8);
                 u32* ri = A.top<u32>(ps.rtotal + 8);
                 SAB_ARENA_CHECK(A);
-                SAB_TRY(sab_comm_exchange(cm, st, ps, rp, rp, sizeof(u32)));
-                SAB_TRY(sab_comm_exchange(cm, st, ps, ri, ri, sizeof(u32)));
+                SAB_TRY(sab_comm_exchange(cm, st, ps, kp, rp, sizeof(u32)));
+                SAB_TRY(sab_comm_exchange(cm, st, ps, vp, ri, sizeof(u32)));
                 if (ps.rtotal) {
                     SAB_LAUNCH(dist_store_sa_kernel, (unsigned)div_up64(ps.rtotal, 256), 256, 0, st, (const u32*)rp, (const u32*)ri,
                                ps.rtotal, (u32)sa_off, sa_local);
                     SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
                 }
                 A.hi = mark2;
             }
-            // e. changed ranks to their owners
+            // e. changed ranks to their owners; the same count exchange returns every rank's number of survivors
             ph.mark(12);
-            SAB_TRY(R_.send_ranks(upd_idx, upd_r, m));
+            u64 rows_k[SAB_MAX_RANKS * 32];
+            SAB_TRY(R_.send_ranks(upd_idx, upd_r, m, d_m, 1, rows_k));
+            u64 kept = rows_k[(size_t)g * (P + 1) + P];
+            tot = 0;
+            for (int s2 = 0; s2 < P; ++s2) tot += rows_k[(size_t)s2 * (P + 1) + P];
+            if (m && sorted_in != 0 && kept > 0)
+                SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1], rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
             A.hi = topmark;
             rb.cur ^= 1;
             m = kept;
-            u64 t1 = m;
-            SAB_TRY(sab_comm_sum_u64(cm, st, &t1, 1));
-            tot = t1;
             S.active[round] = m;
             ds->active[round] = tot;
             h *= 2;
@@ -955,6 +1092,7 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
         sab_set_error("sab200_saca_sharded: bad arguments (n=%llu)", (unsigned long long)n);
         return SAB_ERR_ARGS;
     }
+    const double w0 = now_ms();
     SabContext* c = sab_get_context(cm->device);
     if (!c) return SAB_ERR_CUDA;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -982,7 +1120,9 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     }
     cudaEventRecord(e1, st);
     DistResult res;
+    const double w1 = now_ms();
     int rc = sab_dist_saca(cm, c, A, d_text, shard_len, n, &res, &ds);
+    const double w2 = now_ms();
     if (rc != SAB_OK) {
         cudaMemsetAsync(c->d_ticket, 0, sizeof(u32) * 4, st);  // a failed launch may have left the ticket out of step
         cudaStreamSynchronize(st);
@@ -1025,6 +1165,9 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     c->event_pool.push_back(e3);
     sab_prof_collect(c);
     g_last_stats = c->stats;
+    ds.wall_ms = now_ms() - w0;
+    ds.host_setup_ms = w1 - w0;
+    ds.host_finish_ms = (w2 - w1) - ds.total_ms;  // host time of the construction that its stream did not cover
     return SAB_OK;
 }
 

@@ -172,8 +172,7 @@ struct SplitterDigit {  // destination rank of a key: number of splitters <= key
     int np;
     __device__ __forceinline__ u32 operator()(u64 k) const {
         u32 d = 0;
-#pragma unroll
-        for (int i = 0; i < SAB_MAX_RANKS - 1; ++i) d += (i < np && s[i] <= k) ? 1u : 0u;
+        for (int i = 0; i < np; ++i) d += (s[i] <= k) ? 1u : 0u;  // np is uniform: 1 compare on 2 GPUs, 7 on 8
         return d;
     }
 };
