@@ -40,6 +40,7 @@ struct sab200_comm {
         bool ipc = false;
     } peers[SAB_MAX_RANKS];
     bool peers_ok = false;
+    size_t last_want = 0;  // arena request of the previous construction on this communicator
 };
 #define SAB_COMM_SCRATCH ((size_t)1 << 20)
 
@@ -113,6 +114,18 @@ static int sab_comm_alloc_scratch(sab200_comm* cm) {
     SAB_CUDA_TRY(cudaMalloc(&cm->d_small, SAB_COMM_SCRATCH));
     SAB_CUDA_TRY(cudaMallocHost(&cm->h_small, SAB_COMM_SCRATCH));
     return SAB_OK;
+}
+
+// Unmaps the peers' arenas (before any rank re-allocates its own: memory exported over CUDA IPC is only returned
+// to the device once every importer has closed its mapping).
+static void sab_comm_close_peers(sab200_comm* cm) {
+#ifndef SAB_EMU
+    for (int i = 0; i < SAB_MAX_RANKS; ++i) {
+        if (cm->peers[i].ipc && cm->peers[i].base) cudaIpcCloseMemHandle(cm->peers[i].base);
+        cm->peers[i] = sab200_comm::Peer();
+    }
+#endif
+    cm->peers_ok = false;
 }
 
 static void sab_comm_free(sab200_comm* cm) {

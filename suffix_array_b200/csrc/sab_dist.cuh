@@ -276,9 +276,12 @@ static inline int sab_env_int(const char* name, int dflt) {
 
 // Arena for a rank that owns B text positions: sized for slices up to ~1.3 B records with all suffixes active,
 // capped by the free device memory (a grow-only arena: no cudaMalloc in steady state).
-static int sab_dist_reserve(SabContext* c, u64 B) {
+static inline size_t sab_dist_want(u64 B) {
     const size_t recs = (size_t)(B + B / 3) + ((size_t)1 << 20);
-    size_t want = recs * 72 + ((size_t)256 << 20);
+    return recs * 72 + ((size_t)256 << 20);
+}
+static int sab_dist_reserve(SabContext* c, u64 B) {
+    size_t want = sab_dist_want(B);
     if (c->arena_bytes >= want || c->arena_want_seen == want) return SAB_OK;  // steady state: no driver call at all
     c->arena_want_seen = want;
     size_t free_b = 0, total_b = 0;
@@ -1102,6 +1105,14 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     sab200_dist_stats& ds = cm->last;
     memset(&ds, 0, sizeof(ds));
     const u64 B = n ? div_up64(n, (u64)cm->P) : 1;
+    if (cm->last_want != sab_dist_want(B)) {
+        // another text size than last time (every rank sees the same change): arenas may be re-allocated, so all
+        // peer mappings are closed first, on every rank, before anybody frees
+        cm->last_want = sab_dist_want(B);
+        sab_comm_close_peers(cm);
+        u64 z = 0;
+        SAB_TRY(sab_comm_sum_u64(cm, c->stream, &z, 1));
+    }
     SAB_TRY(sab_dist_reserve(c, B));
     DistArena A;
     A.base = c->arena;

@@ -120,7 +120,9 @@ static inline PackPow sab_pack_pow(u32 radix, int k) {
 __global__ void __launch_bounds__(SAB_PACK_THREADS)
 pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k, PackPow pw,
                  u64* __restrict__ keys) {
-    SAB_SHARED_ARRAY(u16, s_code, SAB_PACK_TILE + 64);
+    // one code per 32-bit word, one pad word per 32: a thread reads its window at a stride of SAB_PACK_ITEMS words
+    // from its neighbour's, which a packed u16 array serves with 4-way bank conflicts
+    SAB_SHARED_ARRAY(u32, s_code, SAB_PACK_TILE + 64 + (SAB_PACK_TILE + 64) / 32 + 8);
     SAB_SHARED_ARRAY(u16, s_lut, 256);
     SAB_SHARED_ARRAY(u32, s_lo, SAB_PACK_TILE + SAB_PACK_TILE / 32 + 8);
     SAB_SHARED_ARRAY(u32, s_hi, SAB_PACK_TILE + SAB_PACK_TILE / 32 + 8);
@@ -129,7 +131,7 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
     const u64 tile0 = (u64)blockIdx.x * SAB_PACK_TILE;
     for (int o = threadIdx.x; o < SAB_PACK_TILE + 64; o += SAB_PACK_THREADS) {
         const u64 i = tile0 + o;
-        s_code[o] = i < n ? s_lut[text[i]] : (u16)0;
+        s_code[SAB_PAD(o)] = i < n ? (u32)s_lut[text[i]] : 0u;
     }
     __syncthreads();
     const int o0 = threadIdx.x * SAB_PACK_ITEMS;
@@ -137,12 +139,12 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
     // first key: independent multiplies by the symbol weights (a Horner chain would serialise k 64-bit multiplies)
     u64 key = 0;
 #pragma unroll 4
-    for (int t = 0; t < k; ++t) key += (u64)s_code[o0 + t] * pw.p[t];
+    for (int t = 0; t < k; ++t) key += (u64)s_code[SAB_PAD(o0 + t)] * pw.p[t];
 #pragma unroll
     for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
         s_lo[SAB_PAD(o0 + j)] = (u32)key;
         s_hi[SAB_PAD(o0 + j)] = (u32)(key >> 32);
-        key = (key - (u64)s_code[o0 + j] * top) * radix + (u64)s_code[o0 + j + k];
+        key = (key - (u64)s_code[SAB_PAD(o0 + j)] * top) * radix + (u64)s_code[SAB_PAD(o0 + j + k)];
     }
     __syncthreads();
 #pragma unroll
