@@ -207,9 +207,23 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
         else k = mid;
     }
     if (MODE == 0) {
-        // upper bound: first index >= i whose suffix does not start with pat   (src/sa.rs:192-201)
+        // upper bound: first index >= i whose suffix does not start with pat   (src/sa.rs:192-201).
+        // The reference bisects [i, hi); the matches are a contiguous run starting at i and usually a short one,
+        // so the same index is found by galloping from i (1, 2, 4, ... while the probe still matches) and
+        // bisecting the last gap: ~2 log2(run) + 1 probes instead of log2(bucket).
         u64 j = i;
         k = hi;
+        for (u64 step = 1; j < k; step <<= 1) {
+            const u64 t = (k - j > step) ? j + step - 1 : k - 1;
+            u32 less_at;
+            const u64 d = group_compare<G>(a, pat, m, a.sa[t], gmask, gl, gbase, pw0, pw1, &less_at);
+            if (d == m) {
+                j = t + 1;
+            } else {
+                k = t;
+                break;
+            }
+        }
         while (j < k) {
             const u64 mid = j + (k - j) / 2;
             const u64 p = a.sa[mid];
