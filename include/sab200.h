@@ -95,6 +95,13 @@ int32_t sab200_enable_buckets(const uint8_t* s, uint64_t n, uint32_t* bkt);
  * sa_len != n+1, src/sa.rs:73-75, or an entry exceeds n, where the reference would panic), <0 error. */
 int32_t sab200_check(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len);
 
+/* ---- LCP array -----------------------------------------------------------------------------
+ * No reference counterpart (README.md:18-23 declines the enhanced suffix array): lcp[0] = 0
+ * and lcp[j] = utils::lcp(&s[sa[j-1]..], &s[sa[j]..]) (src/utils.rs:2-7) for j = 1..n.  `sa` must be the suffix
+ * array of `s` (n + 1 entries); host buffers.  Kasai's recurrence in chunks of consecutive text positions: the
+ * first position of a chunk compares from scratch, the others extend the previous length minus one. */
+int32_t sab200_lcp_array(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len, uint32_t* lcp);
+
 /* ---- batched queries -----------------------------------------------------------------------
  * A resident copy of (text, SA, optional bucket table) on `ngpus` GPUs (replicated; queries are
  * sharded across the replicas, no collective).  bkt_or_null = NULL means "buckets not enabled"

@@ -187,6 +187,15 @@ class SuffixArray {
         return Range{st, en};
     }
 
+    // LCP array of the suffix array (no reference counterpart; README.md:18-23): lcp[0] = 0, lcp[j] = common prefix
+    // of the suffixes sa[j-1] and sa[j]
+    std::vector<std::uint32_t> lcp_array() const {
+        std::vector<std::uint32_t> out(sa_.size());
+        if (sab200_lcp_array(s_, n_, sa_.data(), sa_.size(), out.data()) != 0)
+            throw std::runtime_error(std::string("sab200_lcp_array: ") + sab200_last_error());
+        return out;
+    }
+
     const std::vector<std::uint32_t>& sa() const { return sa_; }   // From<SuffixArray> for Vec<u32>, src/sa.rs:364-368
     const std::uint8_t* as_ref() const { return s_; }              // AsRef<[u8]>, src/sa.rs:370-374
     const std::vector<std::uint32_t>* buckets() const { return has_bkt_ ? &bkt_ : nullptr; }

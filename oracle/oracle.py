@@ -38,6 +38,8 @@ def lib():
             f = getattr(L, name)
             f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
             f.restype = C.c_int
+        L.oracle_lcp_array.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.oracle_lcp_array.restype = C.c_int
         L.oracle_enable_buckets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_enable_buckets.restype = None
         for name in ("oracle_get_bucket", "oracle_get_top_bucket"):
@@ -105,6 +107,14 @@ def sufcheck(s, sa):
     t = _bytes(s)
     sa = np.ascontiguousarray(sa, dtype=np.uint32)
     return lib().oracle_sufcheck(_p(t), t.size, _p(sa), sa.size) == 1
+
+
+def lcp_array(s, sa):
+    t = _bytes(s)
+    sa = np.ascontiguousarray(sa, dtype=np.uint32)
+    out = np.empty(sa.size, dtype=np.uint32)
+    assert lib().oracle_lcp_array(_p(t), t.size, _p(sa), _p(out)) == 0
+    return out
 
 
 def enable_buckets(s):

@@ -126,6 +126,7 @@ def _bind(L):
     _opt = {
         "sab200_enable_buckets": ([vp, u64, vp], i32),
         "sab200_check": ([vp, u64, vp, u64], i32),
+        "sab200_lcp_array": ([vp, u64, vp, u64, vp], i32),
         "sab200_index_create": ([vp, u64, vp, u64, vp, i32], vp),
         "sab200_index_destroy": ([vp], None),
         "sab200_search_all_batch": ([vp, vp, vp, u64, vp, vp], i32),

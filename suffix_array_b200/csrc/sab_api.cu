@@ -386,6 +386,36 @@ extern "C" int32_t sab200_check(const uint8_t* s, uint64_t n, const uint32_t* sa
     return c->h_small[0] ? 0 : 1;
 }
 
+// ---- LCP array ------------------------------------------------------------------------------
+extern "C" int32_t sab200_lcp_array(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len, uint32_t* lcp) {
+    if (!sa || !lcp || (n > 0 && !s) || n > SAB200_MAX_LENGTH || sa_len != n + 1) {
+        sab_set_error("sab200_lcp_array: bad arguments (n=%llu, sa_len=%llu)", (unsigned long long)n, (unsigned long long)sa_len);
+        return SAB_ERR_ARGS;
+    }
+    SabContext* c = sab_get_context(0);
+    if (!c) return SAB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const size_t text_bytes = sab_align_up((size_t)n + 64, 256);
+    const size_t arr_bytes = sab_align_up(((size_t)n + 2) * sizeof(u32), 256);
+    SAB_TRY(sab_arena_reserve(c, text_bytes + 3 * arr_bytes + 1024));
+    u8* d_s = (u8*)c->arena;
+    u32* d_sa = (u32*)(c->arena + text_bytes);
+    u32* d_isa = (u32*)(c->arena + text_bytes + arr_bytes);
+    u32* d_lcp = (u32*)(c->arena + text_bytes + 2 * arr_bytes);
+    cudaStream_t st = c->stream;
+    if (n) SAB_CUDA_TRY(cudaMemcpyAsync(d_s, s, n, cudaMemcpyHostToDevice, st));
+    SAB_CUDA_TRY(cudaMemcpyAsync(d_sa, sa, sa_len * sizeof(u32), cudaMemcpyHostToDevice, st));
+    SAB_LAUNCH(lcp_isa_kernel, (unsigned)div_up64(sa_len, 256), 256, 0, st, (const u32*)d_sa, sa_len, d_isa);
+    SAB_LAUNCH_CHECK();
+    const u64 chunks = div_up64(n ? n : 1, SAB_LCP_CHUNK);
+    SAB_LAUNCH(lcp_kasai_kernel, (unsigned)div_up64(chunks, 256), 256, 0, st, (const u8*)d_s, n, (const u32*)d_sa, (const u32*)d_isa, d_lcp);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaMemcpyAsync(lcp, d_lcp, sa_len * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    return SAB_OK;
+}
+
 // ---- resident index + batched queries ------------------------------------------------------
 struct SabReplica {
     SabContext* ctx = nullptr;

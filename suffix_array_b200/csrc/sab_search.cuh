@@ -282,6 +282,45 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
     }
 }
 
+// ------------------------------------------------------------------ LCP array (Kasai in chunks)
+#define SAB_LCP_CHUNK 32
+__global__ void __launch_bounds__(256) lcp_isa_kernel(const u32* __restrict__ sa, u64 len, u32* __restrict__ isa) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < len) isa[sa[j]] = (u32)j;
+}
+// common prefix of the suffixes at a and b (a != b), known to be at least h: 8 bytes per step while both have them
+__device__ __forceinline__ u64 lcp_extend(const u8* __restrict__ s, u64 n, u64 a, u64 b, u64 h) {
+    while (a + h + 8 <= n && b + h + 8 <= n) {
+        u64 x = 0, y = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            x |= (u64)s[a + h + t] << (8 * t);
+            y |= (u64)s[b + h + t] << (8 * t);
+        }
+        const u64 d = x ^ y;
+        if (d) return h + (u64)((__ffsll((long long)d) - 1) >> 3);
+        h += 8;
+    }
+    while (a + h < n && b + h < n && s[a + h] == s[b + h]) ++h;
+    return h;
+}
+// thread t owns text positions [t*CHUNK, (t+1)*CHUNK): lcp[isa[i]] = common prefix of suffix i and its
+// predecessor in suffix order, each length starting from the previous one minus one
+__global__ void __launch_bounds__(256)
+lcp_kasai_kernel(const u8* __restrict__ s, u64 n, const u32* __restrict__ sa, const u32* __restrict__ isa, u32* __restrict__ lcp) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 i0 = t * SAB_LCP_CHUNK;
+    if (t == 0) lcp[0] = 0;
+    u64 h = 0;
+    for (u64 i = i0; i < i0 + SAB_LCP_CHUNK && i < n; ++i) {
+        const u32 j = isa[i];
+        const u64 p = sa[j - 1];
+        h = lcp_extend(s, n, i, p, h);
+        lcp[j] = (u32)h;
+        if (h) --h;
+    }
+}
+
 // ------------------------------------------------------------------ linear-time integrity check
 // flags[0] != 0 -> not a suffix array.  isa must be pre-filled with 0xFFFFFFFF.
 __global__ void __launch_bounds__(256)

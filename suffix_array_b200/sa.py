@@ -116,6 +116,16 @@ class SuffixArray:
         self.bkt = bkt
         self._drop_index()
 
+    # ---- LCP array (no reference counterpart: README.md:18-23)
+    def lcp_array(self):
+        """lcp[0] = 0, lcp[j] = length of the common prefix of the suffixes sa[j-1] and sa[j] (utils::lcp,
+        src/utils.rs:2-7), computed on the GPU (chunked Kasai)."""
+        L = _lib.require_gpu()
+        out = np.empty(self.sa.size, dtype=np.uint32)
+        _lib.check(L.sab200_lcp_array(_ptr(self.s), self.s.size, self.sa.ctypes.data_as(C.c_void_p), self.sa.size,
+                                      out.ctypes.data_as(C.c_void_p)), "sab200_lcp_array")
+        return out
+
     # ---- resident index for the query kernels
     def use_gpus(self, ngpus):
         """Replicates the index on `ngpus` GPUs; batched queries are sharded across them."""

@@ -179,6 +179,22 @@ def check_pack(oracle, s):
                 pass
 
 
+def check_lcp(oracle, s):
+    """sab200_lcp_array against the oracle's Kasai (and, for short texts, the definition itself)."""
+    t = bytes(s) if not isinstance(s, np.ndarray) else s.tobytes()
+    sa = SuffixArray(t)
+    got = sa.lcp_array()
+    assert np.array_equal(got, oracle.lcp_array(t, sa.sa)), len(t)
+    if len(t) <= 300:
+        for j in range(1, len(t) + 1):
+            a, b = t[int(sa.sa[j - 1]):], t[int(sa.sa[j]):]
+            k = 0
+            while k < min(len(a), len(b)) and a[k] == b[k]:
+                k += 1
+            assert got[j] == k
+        assert got[0] == 0
+
+
 def random_text(rng):
     """Texts with structure: runs, repeats with mutations, mixtures of unique and repetitive regions."""
     from suffix_array_b200 import gen

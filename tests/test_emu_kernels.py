@@ -51,6 +51,14 @@ def test_emu_queries(emu_backend, oracle):
     pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
 
 
+def test_emu_lcp_array(emu_backend, oracle):
+    rng = np.random.default_rng(12)
+    for s in (b"", b"a", b"banana", b"mississippi" * 3, b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"\x00\xff" * 40):
+        pc.check_lcp(oracle, s)
+    for _ in range(6):
+        pc.check_lcp(oracle, pc.random_text(rng))
+
+
 def test_emu_from_parts(emu_backend, oracle):
     rng = np.random.default_rng(3)
     for n in (0, 1, 2, 50, 3000):

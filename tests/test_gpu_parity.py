@@ -114,6 +114,17 @@ def test_queries_sharded_over_replicas(gpu_lib, oracle):
     pc.check_queries(oracle, s, pats, ngpus=ngpus)
 
 
+def test_lcp_array(gpu_lib, oracle):
+    # LCP-array builder (chunked Kasai on the GPU) against the oracle's Kasai
+    rng = np.random.default_rng(21)
+    for s in (b"", b"a", b"banana", b"mississippi" * 3, b"a" * 5000, b"\x00\xff" * 700):
+        pc.check_lcp(oracle, s)
+    for _ in range(8):
+        pc.check_lcp(oracle, pc.random_text(rng))
+    for s in (gen.dna_like(8 << 20), gen.repetitive(4 << 20, block=1 << 14), gen.mixed(4 << 20), np.full(1 << 16, 65, dtype=np.uint8)):
+        pc.check_lcp(oracle, s)
+
+
 def test_pack_correctness(gpu_lib, oracle):
     # src/tests.rs:63-76 (feature "pack") + byte equality with the oracle's restatement of the format
     rng = np.random.default_rng(5)
