@@ -76,6 +76,11 @@ typedef struct sab200_stats {
  * The reference panics when n > MAX_LENGTH (src/saca.rs:10); this returns SAB200_ERR_ARGS. */
 int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus);
 
+/* SuffixArray::new followed by enable_buckets (src/sa.rs:23-27, 89-119) in one call: the bucket table falls out
+ * of the construction's sorted initial keys (65 793 binary searches: no pass over the text, no second upload;
+ * SURVEY.md 8f N2).  `bkt` receives SAB200_BKT_LEN entries, bit-identical to sab200_enable_buckets. */
+int32_t sab200_saca_buckets(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* bkt, int32_t ngpus);
+
 /* Same computation with DEVICE buffers already resident on `device` (no copies): d_s holds n
  * bytes, d_sa receives n+1 entries.  Used to time the device pipeline without PCIe. */
 int32_t sab200_saca_device(const uint8_t* d_s, uint64_t n, uint32_t* d_sa, int32_t device);

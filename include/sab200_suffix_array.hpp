@@ -187,6 +187,18 @@ class SuffixArray {
         return Range{st, en};
     }
 
+    // new() + enable_buckets() (src/sa.rs:23-27, 89-119) in one library call
+    static SuffixArray with_buckets(const std::uint8_t* s, std::size_t n, int ngpus = 1) {
+        std::vector<std::uint32_t> sa(n + 1, 0u);
+        std::vector<std::uint32_t> bkt(SAB200_BKT_LEN, 0u);
+        if (sab200_saca_buckets(s, n, sa.data(), bkt.data(), ngpus) != 0)
+            throw std::runtime_error(std::string("sab200_saca_buckets: ") + sab200_last_error());
+        SuffixArray r(s, n, std::move(sa));
+        r.bkt_ = std::move(bkt);
+        r.has_bkt_ = true;
+        return r;
+    }
+
     // LCP array of the suffix array (no reference counterpart; README.md:18-23): lcp[0] = 0, lcp[j] = common prefix
     // of the suffixes sa[j-1] and sa[j]
     std::vector<std::uint32_t> lcp_array() const {

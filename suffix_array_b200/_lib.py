@@ -125,6 +125,7 @@ def _bind(L):
     L.sab200_shutdown.restype = None
     _opt = {
         "sab200_enable_buckets": ([vp, u64, vp], i32),
+        "sab200_saca_buckets": ([vp, u64, vp, vp, i32], i32),
         "sab200_check": ([vp, u64, vp, u64], i32),
         "sab200_lcp_array": ([vp, u64, vp, u64, vp], i32),
         "sab200_index_create": ([vp, u64, vp, u64, vp, i32], vp),

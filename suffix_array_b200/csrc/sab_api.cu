@@ -228,7 +228,7 @@ static int run_device(SabContext* c, const u8* d_s, u64 n, u32* d_sa) {
     return rc;
 }
 
-static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P);  // sab_dist.cuh
+static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P, u32* bkt);  // sab_dist.cuh
 static void sab_multi_shutdown();
 
 // ------------------------------------------------------------------ extern "C"
@@ -248,7 +248,19 @@ int32_t sab200_saca_device(const uint8_t* d_s, uint64_t n, uint32_t* d_sa, int32
     return rc;
 }
 
-int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
+static int32_t saca_host(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* bkt, int32_t ngpus);
+
+int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) { return saca_host(s, n, sa, nullptr, ngpus); }
+
+int32_t sab200_saca_buckets(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* bkt, int32_t ngpus) {
+    if (!bkt) {
+        sab_set_error("sab200_saca_buckets: bkt is null");
+        return SAB_ERR_ARGS;
+    }
+    return saca_host(s, n, sa, bkt, ngpus);
+}
+
+static int32_t saca_host(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* bkt, int32_t ngpus) {
     if (ngpus == 0) ngpus = sab200_device_count() > SAB_MAX_RANKS ? SAB_MAX_RANKS : sab200_device_count();
     if (!sa || (n > 0 && !s) || n > SAB200_MAX_LENGTH || ngpus < 0 || ngpus > SAB_MAX_RANKS) {
         sab_set_error("sab200_saca: bad arguments (n=%llu, ngpus=%d)", (unsigned long long)n, (int)ngpus);
@@ -262,7 +274,8 @@ int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
         sab_set_error("sab200_saca: %d GPUs requested, %d visible", (int)ngpus, (int)sab200_device_count());
         return SAB_ERR_ARGS;
     }
-    if (ngpus > 1) return sab_saca_multi(s, n, sa, ngpus);
+    if (bkt && n < ((u64)1 << 20)) ngpus = 1;  // tiny texts may pack a single symbol per key: the table then needs the text
+    if (ngpus > 1) return sab_saca_multi(s, n, sa, ngpus, bkt);
     SabContext* c = sab_get_context(0);
     if (!c) return SAB_ERR_CUDA;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -271,16 +284,28 @@ int32_t sab200_saca(const uint8_t* s, uint64_t n, uint32_t* sa, int32_t ngpus) {
     const size_t text_bytes = sab_align_up((size_t)n + 64, 256);
     const size_t sa_bytes = sab_align_up(((size_t)n + 1) * sizeof(u32), 256);
     const size_t work = sab_saca_workspace_bytes(n);
-    SAB_TRY(sab_arena_reserve(c, work + text_bytes + sa_bytes + 512));
+    const size_t bkt_bytes = sab_align_up((size_t)SAB200_BKT_LEN * sizeof(u32), 256);
+    SAB_TRY(sab_arena_reserve(c, work + text_bytes + sa_bytes + bkt_bytes + 512));
     u8* d_s = (u8*)(c->arena + sab_align_up(work, 256));
     u32* d_sa = (u32*)((char*)d_s + text_bytes);
+    u32* d_bkt = (u32*)((char*)d_sa + sa_bytes);
+    c->want_bkt = bkt ? d_bkt : nullptr;
+    c->bkt_add_one = 1;
     double t0 = now_ms();
     if (n) SAB_CUDA_TRY(cudaMemcpyAsync(d_s, s, n, cudaMemcpyHostToDevice, c->stream));
     SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     double t1 = now_ms();
     int rc = run_device(c, d_s, n, d_sa);
+    c->want_bkt = nullptr;
     if (rc == SAB_OK) {
         double t2 = now_ms();
+        if (bkt) {
+            if (n == 0) {
+                for (u32 i = 0; i < SAB200_BKT_LEN; ++i) bkt[i] = 1;  // src/sa.rs:98,112-116 on an empty text
+            } else {
+                SAB_CUDA_TRY(cudaMemcpyAsync(bkt, d_bkt, (size_t)SAB200_BKT_LEN * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
         SAB_CUDA_TRY(cudaMemcpyAsync(sa, d_sa, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->stats.h2d_ms = t1 - t0;

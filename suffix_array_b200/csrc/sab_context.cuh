@@ -66,7 +66,9 @@ struct SabContext {
     char* arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;
-    size_t arena_want_seen = 0;  // request the arena was last sized for (it may have been capped by the free memory)
+    size_t arena_want_seen = 0;
+    u32* want_bkt = nullptr;     // device buffer for the fused bucket table of the running construction (or null)
+    u32 bkt_add_one = 1;  // request the arena was last sized for (it may have been capped by the free memory)
     // profiling
     bool profiling = false;
     std::vector<SabEventPair> events;

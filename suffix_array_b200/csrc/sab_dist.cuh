@@ -606,6 +606,7 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     // ---- 6. ranks, slice of sa[], active list, bucket directory over the slice's keys
     ph.mark(5);
     const u64* sortedK = buf.k[buf.cur];
+    if (c->want_bkt) SAB_TRY(sab_fused_buckets(c, d_text, n, sortedK, R, (const u16*)d_lut, sigma, base, k));  // this slice's share
     const u32* sortedI = sa_written ? sa_local : buf.v[buf.cur];
     u64* freeK = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
@@ -1089,8 +1090,11 @@ extern "C" int32_t sab200_comm_stats(sab200_comm* cm, sab200_dist_stats* out) {
 
 // ------------------------------------------------------------------ one rank of a sharded construction
 // host_out_base != null: the slice is copied to host_out_base + sa_off (the caller's whole sa[] array)
+// h_bkt_part != null: this rank's share of the fused bucket table (SAB200_BKT_LEN counts, host) -- the caller adds the
+// shares of all ranks and 1 for the empty suffix
 static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 n, int shard_on_device, u32* out, u64 out_cap,
-                           int out_on_device, u32* host_out_base, u64* slice_len, u64* sa_off, const u32** d_slice) {
+                           int out_on_device, u32* host_out_base, u64* slice_len, u64* sa_off, const u32** d_slice,
+                           u32* h_bkt_part = nullptr) {
     if (!cm || (shard_len > 0 && !shard) || n > SAB200_MAX_LENGTH) {
         sab_set_error("sab200_saca_sharded: bad arguments (n=%llu)", (unsigned long long)n);
         return SAB_ERR_ARGS;
@@ -1130,10 +1134,20 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
         d_text = t;
     }
     cudaEventRecord(e1, st);
+    u32* d_bkt = nullptr;
+    if (h_bkt_part) {
+        d_bkt = A.bot<u32>((size_t)SAB200_BKT_LEN + 8);
+        SAB_ARENA_CHECK(A);
+        SAB_CUDA_TRY(cudaMemsetAsync(d_bkt, 0, (size_t)SAB200_BKT_LEN * sizeof(u32), st));
+    }
+    c->want_bkt = d_bkt;
+    c->bkt_add_one = 0;
     DistResult res;
     const double w1 = now_ms();
     int rc = sab_dist_saca(cm, c, A, d_text, shard_len, n, &res, &ds);
     const double w2 = now_ms();
+    c->want_bkt = nullptr;
+    c->bkt_add_one = 1;
     if (rc != SAB_OK) {
         cudaMemsetAsync(c->d_ticket, 0, sizeof(u32) * 4, st);  // a failed launch may have left the ticket out of step
         cudaStreamSynchronize(st);
@@ -1144,6 +1158,7 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     if (sa_off) *sa_off = res.sa_off;
     if (d_slice) *d_slice = res.d_slice;
     cudaEventRecord(e2, st);
+    if (h_bkt_part) SAB_CUDA_TRY(cudaMemcpyAsync(h_bkt_part, d_bkt, (size_t)SAB200_BKT_LEN * sizeof(u32), cudaMemcpyDeviceToHost, st));
     if (host_out_base) {
         if (res.slice_len)
             SAB_CUDA_TRY(cudaMemcpyAsync(host_out_base + res.sa_off, res.d_slice, res.slice_len * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -1257,22 +1272,32 @@ static int sab_multi_comms(int P) {
 #endif
 }
 
-static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P) {
+static int sab_saca_multi(const u8* s, u64 n, u32* sa, int P, u32* bkt) {
     std::lock_guard<std::mutex> lk(g_multi_mu);
     SAB_TRY(sab_multi_comms(P));
     std::vector<int> rcs(P, SAB_OK);
     std::vector<std::thread> th;
+    std::vector<u32> parts;
+    if (bkt) parts.assign((size_t)P * SAB200_BKT_LEN, 0u);
     const u64 B = n ? div_up64(n, (u64)P) : 1;
     for (int g = 0; g < P; ++g) {
         th.emplace_back([&, g]() {
             const u64 lo = (u64)g * B < n ? (u64)g * B : n;
             const u64 hi = lo + B < n ? lo + B : n;
             const u64 len = (n - lo) < (hi - lo) + SAB200_SHARD_HALO ? (n - lo) : (hi - lo) + SAB200_SHARD_HALO;
-            rcs[g] = sab_sharded_run(g_multi_comms[g], s + lo, len, n, 0, nullptr, 0, 0, sa, nullptr, nullptr, nullptr);
+            rcs[g] = sab_sharded_run(g_multi_comms[g], s + lo, len, n, 0, nullptr, 0, 0, sa, nullptr, nullptr, nullptr,
+                                     bkt ? parts.data() + (size_t)g * SAB200_BKT_LEN : nullptr);
         });
     }
     for (auto& t : th) t.join();
     if (n == 0) sa[0] = 0;
+    if (bkt) {  // inclusive boundaries: the slices' shares add up; + 1 for the empty suffix (src/sa.rs:98)
+        for (u32 i = 0; i < SAB200_BKT_LEN; ++i) {
+            u32 v = 1;
+            for (int g = 0; g < P; ++g) v += parts[(size_t)g * SAB200_BKT_LEN + i];
+            bkt[i] = v;
+        }
+    }
     for (int g = 0; g < P; ++g)
         if (rcs[g] != SAB_OK) return rcs[g];
     return SAB_OK;

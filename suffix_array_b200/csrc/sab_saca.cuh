@@ -209,6 +209,50 @@ fill_settled_ranks_kernel(const u64* __restrict__ K, const u32* __restrict__ I, 
     if (head && next_head) rank[I[j]] = (u32)j + 1u;
 }
 
+// ------------------------------------------------------------------ 4c. bucket table from the sorted keys
+// enable_buckets (/root/reference/src/sa.rs:89-119) counts 2-byte prefixes in a pass over the text.  Inside a
+// construction that pass is free: the initial keys are sorted and start with the same two symbols (codes in
+// byte order, 0 = end of text), so the inclusive right boundary of a bucket is one lower bound on the sorted key
+// array -- 65 793 binary searches, no pass over the text, no second upload.  Needs k >= 2 symbols per key.
+//   out[slot] = (add_one ? 1 : 0) + #keys whose 2-symbol prefix is <= the slot's   (slot layout: src/sa.rs:94,103,107)
+// add_one accounts for the empty suffix (src/sa.rs:98); a multi-GPU rank passes 0 and the host adds the slices up.
+__global__ void __launch_bounds__(256)
+bucket_from_keys_kernel(const u64* __restrict__ sorted_keys, u64 cnt, const u16* __restrict__ lut, u32 base, u64 unit /* base^(k-2) */,
+                        u32 add_one, u32* __restrict__ out) {
+    SAB_SHARED_ARRAY(u16, s_le, 256);  // number of byte values <= c present in the text (= code of c when present)
+    SAB_SHARED_ARRAY(u16, s_code, 256);
+    {
+        const u32 c = threadIdx.x;
+        s_code[c] = lut[c];
+        u32 le = 0;
+        for (u32 b = 0; b <= c; ++b) le += lut[b] ? 1u : 0u;
+        s_le[c] = (u16)le;
+    }
+    __syncthreads();
+    const u32 slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= 65793u) return;
+    if (slot == 0) {
+        out[0] = add_one;  // "$": the empty suffix alone
+        return;
+    }
+    const u32 c0 = (slot - 1u) / 257u, r = (slot - 1u) % 257u;
+    u64 pre;  // 2-symbol prefixes (as numbers in base `base`) below `pre` are inside or before this slot
+    if (!s_code[c0]) pre = ((u64)s_le[c0] + 1ull) * base;                  // absent byte: everything up to the previous present one
+    else pre = (u64)s_code[c0] * base + (r ? (u64)s_le[r - 1u] : 0ull) + 1ull;
+    u64 lo = 0, hi = cnt;
+    if (pre < (u64)base * base) {  // else: every key is below (also avoids base^k = 2^64)
+        const u64 upper = pre * unit;
+        while (lo < hi) {
+            const u64 mid = lo + (hi - lo) / 2;
+            if (sorted_keys[mid] < upper) lo = mid + 1;
+            else hi = mid;
+        }
+    } else {
+        lo = cnt;
+    }
+    out[slot] = add_one + (u32)lo;
+}
+
 // ------------------------------------------------------------------ 5a. gather the second rank
 #define SAB_GATHER_THREADS 256
 #define SAB_GATHER_ITEMS 4
@@ -323,6 +367,43 @@ static void sab_plan_alphabet(const u64* hist, u64 n, u16* lut, u32* sigma_out, 
     *key_bits_out = bits_of_k[k];
 }
 
+__global__ void bucket_pairs_kernel(const u8* __restrict__ text, u64 n, const u16* __restrict__ lut, u32 sigma, int dense,
+                                    u32* __restrict__ cnt);  // sab_search.cuh
+__global__ void bucket_scan_kernel(u32* __restrict__ bkt);
+
+// The bucket table of the running construction into c->want_bkt: from the sorted initial keys (k >= 2), else by
+// the pair-counting kernels over the resident text (tiny texts with large alphabets; single GPU only).
+static int sab_fused_buckets(SabContext* c, const u8* d_text, u64 n, const u64* sortedK, u64 cnt, const u16* d_lut, u32 sigma,
+                             u32 base, int k) {
+    cudaStream_t st = c->stream;
+    if (k >= 2) {
+        SAB_LAUNCH(bucket_from_keys_kernel, (65793u + 255u) / 256u, 256, 0, st, sortedK, cnt, d_lut, base, sab_pow_u64(base, k - 2),
+                   c->bkt_add_one, c->want_bkt);
+        SAB_LAUNCH_CHECK();
+        c->stats.kernel_launches++;
+        return SAB_OK;
+    }
+    if (!c->bkt_add_one) {
+        sab_set_error("fused bucket table: keys of one symbol on a multi-GPU rank");
+        return SAB_ERR_INTERNAL;
+    }
+    SAB_CUDA_TRY(cudaMemsetAsync(c->want_bkt, 0, 65793u * sizeof(u32), st));
+    const size_t tab_bytes = (size_t)sigma * (sigma + 1) * sizeof(u32);
+    const int dense = tab_bytes <= 160 * 1024;
+#ifndef SAB_EMU
+    SAB_CUDA_TRY(cudaFuncSetAttribute(bucket_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+#endif
+    u64 pblocks = div_up64(n, 256 * 64);
+    const u64 pmax = (u64)c->sm_count * ((dense ? tab_bytes : 0) > 64 * 1024 ? 1 : 4);
+    if (pblocks > pmax) pblocks = pmax;
+    SAB_LAUNCH(bucket_pairs_kernel, (unsigned)pblocks, 256, dense ? tab_bytes : 0, st, d_text, n, d_lut, sigma, dense, c->want_bkt);
+    SAB_LAUNCH_CHECK();
+    SAB_LAUNCH(bucket_scan_kernel, 1, 1024, 0, st, c->want_bkt);
+    SAB_LAUNCH_CHECK();
+    c->stats.kernel_launches += 2;
+    return SAB_OK;
+}
+
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
@@ -405,6 +486,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     // 4. ranks, SA skeleton, active list, bucket directory over the sorted keys
     u32* d_m = c->d_counters;
     const u64* sortedK = buf.k[buf.cur];
+    if (c->want_bkt) SAB_TRY(sab_fused_buckets(c, d_text, n, sortedK, n, (const u16*)d_lut, sigma, base, k));
     const u32* sortedI = sa_written ? d_sa + 1 : buf.v[buf.cur];
     u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];

@@ -64,6 +64,21 @@ class SuffixArray:
     def new(cls, s):
         return cls(s)
 
+    @classmethod
+    def new_with_buckets(cls, s, ngpus=1):
+        """new() + enable_buckets() (src/sa.rs:23-27, 89-119) in ONE library call: the bucket table falls out of the
+        construction's sorted keys (sab200_saca_buckets).  ngpus > 1 shards the construction."""
+        t = _as_text(s)
+        assert t.size <= MAX_LENGTH
+        sa = np.zeros(t.size + 1, dtype=np.uint32)
+        bkt = np.empty(BKT_LEN, dtype=np.uint32)
+        L = _lib.require_gpu()
+        _lib.check(L.sab200_saca_buckets(_ptr(t), t.size, sa.ctypes.data_as(C.c_void_p), bkt.ctypes.data_as(C.c_void_p), ngpus),
+                   "sab200_saca_buckets")
+        self = cls(t, _sa=sa)
+        self.bkt = bkt
+        return self
+
     def set(self, s):
         """src/sa.rs:30-33, literally: rebuilds `sa` for the new text but -- as in the reference --
         neither replaces the stored text nor clears the bucket table."""

@@ -179,6 +179,16 @@ def check_pack(oracle, s):
                 pass
 
 
+def check_fused_buckets(oracle, s, ngpus=1):
+    """sab200_saca_buckets: suffix array AND bucket table of one call against the oracle (src/sa.rs:89-119)."""
+    t = bytes(s) if not isinstance(s, np.ndarray) else s.tobytes()
+    sa = SuffixArray.new_with_buckets(t, ngpus=ngpus)
+    assert np.array_equal(sa.sa, oracle.saca(t)), len(t)
+    exp = oracle.enable_buckets(t)
+    bad = np.flatnonzero(sa.bkt != exp)
+    assert bad.size == 0, (len(t), bad[:5], sa.bkt[bad[:5]], exp[bad[:5]])
+
+
 def check_lcp(oracle, s):
     """sab200_lcp_array against the oracle's Kasai (and, for short texts, the definition itself)."""
     t = bytes(s) if not isinstance(s, np.ndarray) else s.tobytes()

@@ -51,6 +51,19 @@ def test_emu_queries(emu_backend, oracle):
     pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
 
 
+def test_emu_fused_buckets(emu_backend, oracle):
+    """Bucket table from the sorted keys of the construction: absent bytes, \\0 / \\xff, one symbol per key (falls
+    back to the pair counting over the resident text), all 256 byte values, 255 values (radix 2^8: base^k = 2^64)."""
+    rng = np.random.default_rng(31)
+    texts = [b"", b"a", b"ab", b"banana", b"\x00", b"\xff\x00\xff", b"mississippi" * 5, bytes(range(256)) * 3,
+             bytes(range(255)) * 40, bytes(range(1, 256)) * 40, rng.integers(0, 256, 70000, dtype=np.uint8),
+             rng.integers(0, 255, 90000, dtype=np.uint8), rng.integers(3, 7, 5000, dtype=np.uint8)]
+    for s in texts:
+        pc.check_fused_buckets(oracle, s)
+    for _ in range(6):
+        pc.check_fused_buckets(oracle, pc.random_text(rng))
+
+
 def test_emu_lcp_array(emu_backend, oracle):
     rng = np.random.default_rng(12)
     for s in (b"", b"a", b"banana", b"mississippi" * 3, b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"\x00\xff" * 40):

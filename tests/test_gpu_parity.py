@@ -114,6 +114,21 @@ def test_queries_sharded_over_replicas(gpu_lib, oracle):
     pc.check_queries(oracle, s, pats, ngpus=ngpus)
 
 
+def test_fused_buckets(gpu_lib, oracle):
+    # new() + enable_buckets() in one call, table from the construction's sorted keys
+    rng = np.random.default_rng(41)
+    texts = [b"", b"a", b"banana", b"\xff\x00\xff", bytes(range(256)) * 3, bytes(range(255)) * 4000, rng.integers(0, 256, 3 << 20, dtype=np.uint8),
+             rng.integers(0, 255, 1 << 20, dtype=np.uint8), gen.dna_like(16 << 20), gen.mixed(8 << 20), gen.repetitive(4 << 20, block=1 << 12)]
+    for s in texts:
+        pc.check_fused_buckets(oracle, s)
+    for _ in range(8):
+        pc.check_fused_buckets(oracle, pc.random_text(rng))
+    ngpus = min(4, gpu_lib.sab200_device_count())
+    if ngpus >= 2:
+        for s in (gen.dna_like(16 << 20), gen.mixed(8 << 20), rng.integers(0, 256, 3 << 20, dtype=np.uint8), b"banana"):
+            pc.check_fused_buckets(oracle, s, ngpus=ngpus)
+
+
 def test_lcp_array(gpu_lib, oracle):
     # LCP-array builder (chunked Kasai on the GPU) against the oracle's Kasai
     rng = np.random.default_rng(21)
