@@ -150,6 +150,24 @@ def cpu_baseline_run(text, sample_bytes):
     return sample.size / 1e6 / dt, dt
 
 
+def cpu_all_cores_run(text, sample_bytes):
+    """The "all cores" column (north_star names psacak, which is not available here): the OpenMP prefix-doubling
+    port of oracle/sa_parallel.cpp with every host thread, on the same prefix as the single-thread figure."""
+    from oracle import oracle
+    sample = np.ascontiguousarray(text[:sample_bytes])
+    try:
+        t0 = time.perf_counter()
+        sa, threads = oracle.saca_parallel(sample)
+        dt = time.perf_counter() - t0
+    except Exception as e:  # noqa: BLE001 -- a box without the OpenMP runtime reports it instead of failing the line
+        return {"unavailable": str(e)[:200]}
+    assert int(sa[0]) == sample.size
+    return {"value": round(sample.size / 1e6 / dt, 3), "unit": "MB/s", "cores": threads, "kind": "port",
+            "sample": "first %d MiB of the same text (%.1f s)" % (sample_bytes >> 20, dt),
+            "note": "OpenMP prefix doubling (oracle/sa_parallel.cpp); psacak, the all-cores SACA north_star names, "
+                    "is not a dependency of the reference and not installable here"}
+
+
 def config_of(workload, n, n_mib):
     desc = WORKLOADS[workload][0]
     return {"workload": desc if not n_mib else "%s at %d MiB" % (workload, n_mib), "text_bytes": n}
@@ -179,6 +197,7 @@ def run_reference(args, rank, world):
     sample = "first %d MiB of the same text per step, oracle SA-IS port, 1 thread" % (sample_bytes >> 20)
     cpu = {"value": round(v, 3), "unit": "MB/s", "cores": 1, "kind": "port", "sample": sample,
            "note": "the reference's libdivsufsort (single thread) is not buildable here (no Rust / crate sources)"}
+    cpu["all_cores"] = cpu_all_cores_run(text, sample_bytes)
     if args.ref_full:
         vf, dtf = cpu_baseline_run(text, n_full)
         cpu["full_size"] = {"value": round(vf, 3), "unit": "MB/s", "seconds": round(dtf, 1), "text_bytes": n_full}
@@ -471,7 +490,8 @@ def main():
         v, dt = cpu_baseline_run(text, sb)
         cpu = {"value": round(v, 3), "unit": "MB/s", "cores": 1, "kind": "port",
                "sample": "first %d MiB of the same text, oracle SA-IS port, 1 thread (%.1f s)" % (sb >> 20, dt),
-               "full_size": (load_profile("r02_reference_full_size.json") or {}).get("full_size")}
+               "full_size": (load_profile("r02_reference_full_size.json") or {}).get("full_size"),
+               "all_cores": cpu_all_cores_run(text, sb)}
     print(json.dumps({
         "metric": METRIC, "value": round(value, 2), "unit": "MB/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms, 3), "higher_is_better": True,
@@ -589,6 +609,9 @@ def dist_case(L, _lib, torch, dist, gloo, comm, rank, local_rank, world, workloa
         sl, off = comm.saca(h_shard, n, out=h_out)
     barrier()
     e2e_ms = allred((time.perf_counter() - t0) * 1e3 / steps, dist.ReduceOp.MAX)
+    es = comm.stats()
+    e2e_parts = {"h2d_ms": round(es["phase_ms"][14], 2), "stream_ms": round(es["total_ms"], 2), "d2h_ms": round(es["phase_ms"][15], 2),
+                 "wall_ms": round(es["wall_ms"], 2)}
     if sampler is not None:
         sampler.end()
     # verification, outside the timed region: slices and shards to rank 0, GPU verifier (+ CPU oracle)
@@ -603,7 +626,7 @@ def dist_case(L, _lib, torch, dist, gloo, comm, rank, local_rank, world, workloa
     max_slice = allred(slice_len, dist.ReduceOp.MAX)
     phases = {nm: round(st["phase_ms"][i], 2) for i, nm in enumerate(sdist.PHASES) if st["phase_ms"][i] > 0}
     rec = {"text_bytes": n, "ms_per_step": round(dev_ms, 3), "value": round(n / 1e6 / (dev_ms / 1e3), 2),
-           "e2e_ms_per_step": round(e2e_ms, 3), "e2e_value": round(n / 1e6 / (e2e_ms / 1e3), 2),
+           "e2e_ms_per_step": round(e2e_ms, 3), "e2e_value": round(n / 1e6 / (e2e_ms / 1e3), 2), "e2e_parts_rank0": e2e_parts,
            "rounds": st["rounds"], "active": st["active"], "lazy_isa": bool(st["lazy_isa"]),
            "rank_layout": "block-cyclic" if st["rank_layout"] else "block", "collectives_per_step": st["collectives"],
            "all_to_all_bytes_per_step": int(a2a), "largest_slice": int(max_slice), "phase_ms_rank0": phases,
@@ -672,7 +695,7 @@ def run_distributed(args, L, _lib, torch, dist, rank, local_rank, world):
                          "frac": round(main_rec["radix_pass_gbs_slowest_rank"] / peak, 4), "traffic": None, "peak_source": peak_src,
                          "share_of_step": main_rec["radix_pass_share_max"]},
             "e2e": {"value": main_rec["e2e_value"], "unit": "MB/s", "ms_per_step": main_rec["e2e_ms_per_step"],
-                    "h2d_bytes_per_step": n + world * sdist.HALO, "d2h_bytes_per_step": 4 * n,
+                    "h2d_bytes_per_step": n + world * sdist.HALO, "d2h_bytes_per_step": 4 * n, "parts_rank0": main_rec["e2e_parts_rank0"],
                     "api": "sab200_saca_sharded (pinned host shard in, pinned host SA slice out, one PCIe link per rank)"},
             "cpu_baseline": None, "gpu_launches": main_rec["gpu_launches"], "verification": main_rec["verification"],
             "verified": main_rec["verified"], "c4": c4, "search": search, "clocks": sampler.summary()}))

@@ -109,6 +109,28 @@ def sufcheck(s, sa):
     return lib().oracle_sufcheck(_p(t), t.size, _p(sa), sa.size) == 1
 
 
+_par = None
+
+
+def saca_parallel(s, threads=0):
+    """All-cores CPU construction (oracle/sa_parallel.cpp, OpenMP): the "all cores" baseline of bench.py.
+    Returns (sa, threads used)."""
+    global _par
+    if _par is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liboracle_par.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", os.path.dirname(path), "liboracle_par.so"], stdout=subprocess.DEVNULL)
+        _par = C.CDLL(path)
+        _par.oracle_saca_parallel.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        _par.oracle_saca_parallel.restype = C.c_int
+        _par.oracle_parallel_threads.restype = C.c_int
+    t = _bytes(s)
+    sa = np.empty(t.size + 1, dtype=np.uint32)
+    rc = _par.oracle_saca_parallel(_p(t), t.size, _p(sa), int(threads))
+    assert rc == 0
+    return sa, (int(threads) if threads else int(_par.oracle_parallel_threads()))
+
+
 def lcp_array(s, sa):
     t = _bytes(s)
     sa = np.ascontiguousarray(sa, dtype=np.uint32)
