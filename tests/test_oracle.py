@@ -171,3 +171,14 @@ def test_pack_layout_against_python_model(oracle):
     for bad in (b"", b"SA4x", _pack_model([1, 0])[:-1], b"XXXX" + _pack_model([1, 0])[4:]):
         with pytest.raises(ValueError):
             oracle.unpack(bad)
+
+
+def test_parallel_cpu_baseline_matches(oracle):
+    """oracle/sa_parallel.cpp (the all-cores CPU baseline of bench.py) against the single-thread oracle."""
+    from suffix_array_b200 import gen
+    rng = np.random.default_rng(77)
+    texts = [b"", b"a", b"banana", b"\x00\x00\x00", b"a\x00", b"a" * 300, b"mississippi" * 9, gen.dna_like(200000).tobytes(),
+             gen.repetitive(100000, block=777, mut_rate=1e-3).tobytes(), rng.integers(0, 256, 50000, dtype=np.uint8).tobytes()]
+    for t in texts:
+        sa, threads = oracle.saca_parallel(t)
+        assert threads >= 1 and np.array_equal(sa, oracle.saca(t)), len(t)
