@@ -199,6 +199,7 @@ int32_t sab200_saca_sharded(sab200_comm* comm, const uint8_t* shard, uint64_t sh
  * 10 round sorts, 11 re-rank, 12 rank updates, 13 new SA entries to their slices, 14 H2D, 15 D2H */
 typedef struct sab200_dist_stats {
     uint32_t nranks, rank, rounds, lazy_isa, rank_layout /* 0 block, 1 block-cyclic */, rebalanced;
+    uint32_t p2p_rounds, fused_exchange; /* rounds without an exchange step (peer loads / stores); key exchange fused into the partition */
     uint64_t slice_len, sa_off, all_to_all_bytes, collectives, resolved_empty;
     uint64_t active[SAB200_MAX_ROUNDS]; /* active suffixes over all ranks entering round r (0 = after the initial sort) */
     double phase_ms[SAB200_PHASES];     /* CUDA events on the rank's stream */

@@ -64,7 +64,7 @@ class DistStats(C.Structure):
     """include/sab200.h sab200_dist_stats"""
     _fields_ = [
         ("nranks", C.c_uint32), ("rank", C.c_uint32), ("rounds", C.c_uint32), ("lazy_isa", C.c_uint32),
-        ("rank_layout", C.c_uint32), ("rebalanced", C.c_uint32),
+        ("rank_layout", C.c_uint32), ("rebalanced", C.c_uint32), ("p2p_rounds", C.c_uint32), ("fused_exchange", C.c_uint32),
         ("slice_len", C.c_uint64), ("sa_off", C.c_uint64), ("all_to_all_bytes", C.c_uint64), ("collectives", C.c_uint64),
         ("resolved_empty", C.c_uint64),
         ("active", C.c_uint64 * MAX_ROUNDS),

@@ -119,6 +119,49 @@ __global__ void find_boundary_kernel(const u32* __restrict__ r1, u64 m, const u6
     if (t < window && p < m && r1[p] != r1[c - 1]) atomicMin(&out[j], (unsigned long long)p);
 }
 
+// ---- peer-to-peer rounds: the arenas of all GPUs are mapped into every rank (sab_peers_update), so a SMALL round
+// needs no exchange step at all: the gather loads rank[i+h] straight from the owner GPU over NVLink (and resolves
+// an EMPTY slot through the owner's text, the slice's directory and sorted keys, all remote loads), the changed
+// ranks are stored straight into the owner's block.  Two stream-ordered all_reduces per round order the phases
+// (every rank has finished reading before anybody writes, and vice versa) and carry the survivor counts.
+struct P2PTable {
+    u32* rank_local[SAB_MAX_RANKS];
+    const u8* text[SAB_MAX_RANKS];
+    const u64* sorted[SAB_MAX_RANKS];
+    const u32* dir[SAB_MAX_RANKS];  // pre-shifted: indexed by key >> dir_shift
+    u64 R[SAB_MAX_RANKS];
+    u64 n_rel[SAB_MAX_RANKS];       // readable text bytes of the shard (own positions + halo)
+    u32 sa_off[SAB_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256)
+dist_gather_p2p_kernel(const u32* __restrict__ r1, const u32* __restrict__ idx, u64 m, u32 h, RankLayout lay, P2PTable pt, int lazy,
+                       const u16* __restrict__ lut, u32 base, int k, int dir_shift, SplitterDigit sd, u64* __restrict__ key64) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const u64 q = (u64)idx[t] + h;
+    const u32 o = lay.owner(q);
+    const u64 slot = lay.slot(q, o);
+    u32 r2 = pt.rank_local[o][slot];
+    if (lazy && r2 == SAB_RANK_EMPTY) {  // block layout: the owner of q holds text position q at offset slot
+        const u64 key = pack_key_at(pt.text[o], pt.n_rel[o], lut, base, k, slot);
+        const u32 d = sd(key);
+        r2 = pt.sa_off[d] + (u32)sorted_key_position(pt.sorted[d], pt.R[d], pt.dir[d], dir_shift, key);
+        pt.rank_local[o][slot] = r2;  // memoise; racing writers store the same value
+    }
+    key64[t] = ((u64)r1[t] << 32) | r2;
+}
+// rank[idx[t]] = val[t] on the owner of idx[t]; idx == 0xFFFFFFFF marks "nothing to write"
+__global__ void __launch_bounds__(256)
+dist_scatter_p2p_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 cnt, RankLayout lay, P2PTable pt) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const u32 i = idx[t];
+    if (i == 0xffffffffu) return;
+    const u32 o = lay.owner(i);
+    pt.rank_local[o][lay.slot(i, o)] = val[t];
+}
+__global__ void put_u64_kernel(u64* dst, const u32* src32) { *dst = *src32; }
+
 // ---- lazy inverse suffix array, distributed (see the file header, step 6)
 __global__ void __launch_bounds__(256)
 dist_lazy_collect_kernel(const u32* __restrict__ q, const u32* __restrict__ ans, u64 count, u32 h, u64 shard_lo,
@@ -788,6 +831,43 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 }
             }
         }
+        // ---- 7c. peer table of the peer-to-peer rounds (same precondition as the fused key exchange)
+        bool p2p_ready = false;
+        P2PTable pt;
+        memset(&pt, 0, sizeof(pt));
+        const u64 p2p_max = (u64)sab_env_int("SAB_P2P_MAX_RECORDS", 16 << 20);  // per rank; above it the all-to-all form wins
+        if (fused && !rebalanced) {
+            // row: offsets of rank_local, text, sorted keys, directory inside the arena; directory origin, slice length, offset
+            u64* hrow = cm->h_small + 32;
+            hrow[0] = (u64)((char*)rank_local - c->arena);
+            hrow[1] = (u64)((const char*)d_text - c->arena);
+            hrow[2] = (u64)((const char*)sortedK - c->arena);
+            hrow[3] = (u64)((char*)dir - c->arena);
+            hrow[4] = dlo;
+            hrow[5] = R;
+            hrow[6] = sa_off;
+            hrow[7] = ((const char*)d_text >= c->arena && (const char*)d_text < c->arena + c->arena_bytes) ? 1 : 0;
+            SAB_CUDA_TRY(cudaMemcpyAsync(cm->d_small, hrow, 8 * sizeof(u64), cudaMemcpyHostToDevice, st));
+            u64 prow[SAB_MAX_RANKS * 8];
+            SAB_TRY(sab_comm_gather_rows(cm, st, 8, prow));  // also orders every rank's ISA scatter before the first gather
+            bool ok = true;
+            for (int d = 0; d < P; ++d) {
+                const u64* r = prow + (size_t)d * 8;
+                char* pb = d == g ? c->arena : (char*)cm->peers[d].base;
+                ok = ok && r[7] == 1 && pb != nullptr;
+                pt.rank_local[d] = (u32*)(pb + r[0]);
+                pt.text[d] = (const u8*)(pb + r[1]);
+                pt.sorted[d] = (const u64*)(pb + r[2]);
+                pt.dir[d] = (const u32*)(pb + r[3]) - r[4];
+                pt.R[d] = r[5];
+                pt.sa_off[d] = (u32)r[6];
+                const u64 lo_d = (u64)d * B < n ? (u64)d * B : n;
+                const u64 hi_d = lo_d + B < n ? lo_d + B : n;
+                pt.n_rel[d] = (n - lo_d) < (hi_d - lo_d) + SAB200_SHARD_HALO ? (n - lo_d) : (hi_d - lo_d) + SAB200_SHARD_HALO;
+            }
+            p2p_ready = ok;
+        }
+        bool lead_barrier = false;  // the first gather is ordered by the row exchange above
         const int rank_bits = sab_ceil_log2_u64(n + 2);
         bool group_sort_on = SAB_GROUP_SORT != 0;
         u64 h = (u64)k;
@@ -799,6 +879,24 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 return SAB_ERR_INTERNAL;
             }
             const size_t topmark = A.hi;
+            // Small rounds go peer to peer (no exchange step, one host round trip); large ones through partition +
+            // all-to-all (bulk NVLink transfers, local random access).  Same decision on every rank.
+            const bool p2p_round = p2p_ready && tot <= p2p_max * (u64)P;
+            if (p2p_round) {
+                ph.mark(8);
+                if (lead_barrier) {  // the owners' scatters of an all-to-all round must have finished everywhere
+                    SAB_TRY(sab_comm_all_reduce_u64(cm, st, cm->d_small + 8, 1));
+                    lead_barrier = false;
+                }
+                if (m) {
+                    sab_prof_begin(c, 4);
+                    SAB_LAUNCH(dist_gather_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, st, (const u32*)r1buf, (const u32*)rb.v[rb.cur], m,
+                               (u32)h, lay, pt, lazy ? 1 : 0, (const u16*)d_lut, base, k, dir_shift, sdop, rb.k[rb.cur]);
+                    sab_prof_end(c);
+                    SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
+                }
+            } else {
             // a. requests i + h to the owners (payload = list position), answers back in the same order
             ph.mark(8);
             u32* cur_idx = rb.v[rb.cur];
@@ -883,6 +981,7 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 SAB_LAUNCH_CHECK();
                 S.kernel_launches++;
             }
+            }  // all-to-all form of steps a, b
             A.hi = topmark;  // requests, answers and look-up buffers are dead (stream order)
 
             // c. order inside the groups (as on one GPU: the list is still grouped by r1, ascending)
@@ -967,13 +1066,35 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
                 }
                 A.hi = mark2;
             }
-            // e. changed ranks to their owners; the same count exchange returns every rank's number of survivors
+            // e. changed ranks to their owners; the same exchange returns every rank's number of survivors
             ph.mark(12);
-            u64 rows_k[SAB_MAX_RANKS * 32];
-            SAB_TRY(R_.send_ranks(upd_idx, upd_r, m, d_m, 1, rows_k));
-            u64 kept = rows_k[(size_t)g * (P + 1) + P];
-            tot = 0;
-            for (int s2 = 0; s2 < P; ++s2) tot += rows_k[(size_t)s2 * (P + 1) + P];
+            u64 kept = 0;
+            if (p2p_round) {
+                // all_reduce #1: the survivors add up (termination) and every rank has finished LOADING ranks;
+                // then the stores go straight into the owners' blocks; all_reduce #2: every store has landed
+                SAB_LAUNCH(put_u64_kernel, 1, 1, 0, st, cm->d_small, (const u32*)d_m);
+                SAB_LAUNCH_CHECK();
+                SAB_TRY(sab_comm_all_reduce_u64(cm, st, cm->d_small, 1));
+                if (m) {
+                    SAB_LAUNCH(dist_scatter_p2p_kernel, (unsigned)div_up64(m, 256), 256, 0, st, (const u32*)upd_idx, (const u32*)upd_r, m, lay, pt);
+                    SAB_LAUNCH_CHECK();
+                    S.kernel_launches++;
+                }
+                SAB_TRY(sab_comm_all_reduce_u64(cm, st, cm->d_small + 8, 1));
+                SAB_CUDA_TRY(cudaMemcpyAsync(cm->h_small, cm->d_small, sizeof(u64), cudaMemcpyDeviceToHost, st));
+                SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small, d_m, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                SAB_CUDA_TRY(cudaStreamSynchronize(st));
+                tot = cm->h_small[0];
+                kept = c->h_small[0];
+                ds->p2p_rounds++;
+            } else {
+                u64 rows_k[SAB_MAX_RANKS * 32];
+                SAB_TRY(R_.send_ranks(upd_idx, upd_r, m, d_m, 1, rows_k));
+                kept = rows_k[(size_t)g * (P + 1) + P];
+                tot = 0;
+                for (int s2 = 0; s2 < P; ++s2) tot += rows_k[(size_t)s2 * (P + 1) + P];
+                lead_barrier = true;
+            }
             if (m && sorted_in != 0 && kept > 0)
                 SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1], rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
             A.hi = topmark;
@@ -996,6 +1117,7 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     ds->lazy_isa = lazy ? 1u : 0u;
     ds->rank_layout = (u32)layout_cyc;
     ds->rebalanced = rebalanced ? 1u : 0u;
+    ds->fused_exchange = fused ? 1u : 0u;
     ds->slice_len = R;
     ds->sa_off = sa_off;
     ds->all_to_all_bytes = cm->bytes_sent;
@@ -1127,10 +1249,13 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     const u8* d_text = shard;
     cudaEvent_t e0 = sab_event_get(c), e1 = sab_event_get(c), e2 = sab_event_get(c), e3 = sab_event_get(c);
     cudaEventRecord(e0, st);
-    if (!shard_on_device) {
+    if (!shard_on_device || (cm->P > 1 && cm->kind == 0)) {
+        // host shard: upload; device shard on a multi-GPU run: a copy inside the arena, which is what the peers have
+        // mapped (the lazy look-ups of the peer-to-peer rounds read the owner's text)
         u8* t = A.bot<u8>((size_t)shard_len + 64);
         SAB_ARENA_CHECK(A);
-        if (shard_len) SAB_CUDA_TRY(cudaMemcpyAsync(t, shard, shard_len, cudaMemcpyHostToDevice, st));
+        if (shard_len)
+            SAB_CUDA_TRY(cudaMemcpyAsync(t, shard, shard_len, shard_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         d_text = t;
     }
     cudaEventRecord(e1, st);

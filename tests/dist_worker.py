@@ -72,9 +72,10 @@ def main():
         if rank == 0:
             exp = oracle.saca(t)
             good = bool(np.array_equal(full, exp))
-            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d collectives=%d rebalanced=%s layout=%s lazy=%s resolved=%d " % (
+            print("n=%d P=%d rounds=%d slices_ok=%s a2a_bytes=%d collectives=%d rebalanced=%s layout=%s lazy=%s resolved=%d p2p_rounds=%d fused=%d " % (
                 n, world, st["rounds"], good, st["all_to_all_bytes"], st["collectives"], bool(st["rebalanced"]),
-                "cyclic" if st["rank_layout"] else "block", bool(st["lazy_isa"]), st["resolved_empty"]), flush=True)
+                "cyclic" if st["rank_layout"] else "block", bool(st["lazy_isa"]), st["resolved_empty"], st["p2p_rounds"],
+                st["fused_exchange"]), flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda" if backend == "nccl" else "cpu")
     dist.broadcast(flag, 0)

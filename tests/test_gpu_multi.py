@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,port,env", [(2, 29621, {}), (2, 29623, {"SAB_DIST_LAZY": "0"}),
+@pytest.mark.parametrize("world,port,env", [(2, 29621, {}), (2, 29623, {"SAB_DIST_LAZY": "0"}), (2, 29626, {"SAB_P2P_MAX_RECORDS": "0"}),
+                                            (2, 29627, {"SAB_DIST_P2P": "0"}), (2, 29628, {"SAB_P2P_MAX_RECORDS": "300000", "SAB_REBALANCE_MIN": "1000"}),
                                             (2, 29624, {"SAB_DIST_LAZY": "0", "SAB_RANK_LAYOUT": "block"}),
                                             (4, 29622, {}), (4, 29625, {"SAB_DIST_FUZZ": "12"})])
 def test_dist_construction_nccl(gpu_lib, world, port, env):
@@ -30,6 +31,14 @@ def test_dist_construction_nccl(gpu_lib, world, port, env):
     assert out.stdout.count("slices_ok=True") == expect, out.stdout
     if not env:
         assert "lazy=True" in out.stdout and "layout=cyclic" in out.stdout, out.stdout
+        lines = out.stdout.splitlines()
+        assert any("fused=1" in l for l in lines), out.stdout                      # key exchange fused into the partition
+        assert any("lazy=True" in l and "p2p_rounds=0" not in l for l in lines), out.stdout   # peer-to-peer rounds, lazy look-ups
+        assert any("lazy=False" in l and "p2p_rounds=0" not in l for l in lines), out.stdout  # ... and with the complete array
+    if env.get("SAB_P2P_MAX_RECORDS") == "0":
+        assert all("p2p_rounds=0" in l for l in out.stdout.splitlines() if "slices_ok" in l), out.stdout
+    if env.get("SAB_DIST_P2P") == "0":
+        assert all("fused=0" in l and "p2p_rounds=0" in l for l in out.stdout.splitlines() if "slices_ok" in l), out.stdout
     if env.get("SAB_DIST_LAZY") == "0":
         assert "lazy=True" not in out.stdout, out.stdout
     if env.get("SAB_RANK_LAYOUT") == "block":
