@@ -51,7 +51,8 @@ struct SabContext {
     u64* d_ghist = nullptr;   // [8][256]
     u64* d_gbase = nullptr;   // [8][256]
     u32* d_skip = nullptr;    // [8]
-    u32* h_small = nullptr;   // pinned, 64 words
+    u32* h_small = nullptr;   // pinned, 4096 words: [0,16) counters read back, [32] sentinel staging, [64,320) byte
+                              // histogram, [384,512) code table staging, [1024,2048) 512 u64 of count / base staging
     u64* d_lookback = nullptr;
     size_t lookback_tiles = 0;
     u32* d_ticket = nullptr;
@@ -61,7 +62,8 @@ struct SabContext {
     ScanSlot* d_scan_slots = nullptr;  // chained-scan status, one 16-byte slot per tile
     size_t scan_tiles = 0;
     u32 scan_epoch = 0;
-    u32* d_counters = nullptr;  // [16] device scalars
+    u32* d_counters = nullptr;  // 1024 words: [0,16) device scalars (counts of the scans), [16,272) byte histogram,
+                                // [272,400) code table (256 x u16)
     // arena
     char* arena = nullptr;
     size_t arena_bytes = 0;

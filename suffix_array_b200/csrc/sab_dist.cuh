@@ -532,7 +532,8 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     u64 splitters[SAB_MAX_RANKS];
     for (int i = 0; i < SAB_MAX_RANKS; ++i) splitters[i] = ~0ull;
     if (P > 1) {
-        const u32 NS = 2048;
+        // ~8 Ki samples over all ranks (slice sizes within a few per cent); the pool is sorted on the host
+        const u32 NS = 8192 / (u32)P < 512 ? 512u : (8192 / (u32)P > 2048 ? 2048u : 8192 / (u32)P);
         const u64 step = count / NS ? count / NS : 1;
         u64* d_sample = cm->d_small;
         SAB_LAUNCH(sample_keys_kernel, (NS + 255) / 256, 256, 0, st, (const u64*)keysA, count, step, NS, d_sample);
@@ -835,7 +836,9 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
         bool p2p_ready = false;
         P2PTable pt;
         memset(&pt, 0, sizeof(pt));
-        const u64 p2p_max = (u64)sab_env_int("SAB_P2P_MAX_RECORDS", 16 << 20);  // per rank; above it the all-to-all form wins
+        // records per rank; above it the all-to-all form wins (measured on 8 B200, 1 GiB text: every round peer to peer
+        // 20.3 ms, limit 2 Mi 18.8 ms; on 2 GPUs limits of 4 Mi .. 16 Mi are within 1 % of each other)
+        const u64 p2p_max = (u64)sab_env_int("SAB_P2P_MAX_RECORDS", 2 << 20);
         if (fused && !rebalanced) {
             // row: offsets of rank_local, text, sorted keys, directory inside the arena; directory origin, slice length, offset
             u64* hrow = cm->h_small + 32;
