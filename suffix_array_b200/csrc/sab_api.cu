@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <new>
+#include <thread>
 
 static_assert(sizeof(SabStats) == sizeof(sab200_stats), "SabStats must mirror sab200_stats");
 static_assert(SAB_MAX_ROUNDS == SAB200_MAX_ROUNDS, "round table size");
@@ -66,6 +67,10 @@ void sab_context_destroy(SabContext* c) {
     cudaFree(c->d_gbase);
     cudaFree(c->d_skip);
     cudaFreeHost(c->h_small);
+    for (int i = 0; i < 2; ++i) {
+        if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
+        if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
+    }
     cudaFree(c->d_lookback);
     cudaFree(c->d_ticket);
     cudaFree(c->d_scan_slots);
@@ -199,6 +204,111 @@ void sab_prof_collect(SabContext* c) {
     c->events.clear();
 }
 
+// ------------------------------------------------------------------ host <-> device copies of caller buffers
+// The seam hands over whatever the caller allocated -- for the Rust crate a plain Vec (pageable memory).  CUDA
+// stages pageable copies through a small internal buffer at 12-15 GB/s; here they go through two pinned bounce
+// buffers of the context instead: the DMA of chunk i+1 (PCIe rate) overlaps the host memcpy of chunk i, which a
+// few threads share.  Pinned / registered caller buffers take the direct path.
+#define SAB_BOUNCE_BYTES ((size_t)32 << 20)
+static int sab_copy_threads() {
+    static int t = 0;
+    if (!t) {
+        int hw = (int)std::thread::hardware_concurrency();
+        t = hw >= 16 ? 6 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
+        const char* e = getenv("SAB_COPY_THREADS");
+        if (e && atoi(e) > 0) t = atoi(e);
+    }
+    return t;
+}
+static void sab_parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const int T = sab_copy_threads();
+    if (T <= 1 || bytes < ((size_t)4 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
+    for (int i = 1; i < T; ++i) {
+        const size_t lo = (size_t)i * per;
+        if (lo >= bytes) break;
+        const size_t len = lo + per < bytes ? per : bytes - lo;
+        th.emplace_back([=]() { memcpy((char*)dst + lo, (const char*)src + lo, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& t : th) t.join();
+}
+static bool sab_is_pageable(const void* p) {
+    const char* f = getenv("SAB_FORCE_STAGED");
+    if (f && *f == '1') return true;
+#ifdef SAB_EMU
+    (void)p;
+    return false;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+#endif
+}
+static int sab_bounce_init(SabContext* c) {
+    if (c->bounce[0]) return SAB_OK;
+    for (int i = 0; i < 2; ++i) {
+        SAB_CUDA_TRY(cudaMallocHost(&c->bounce[i], SAB_BOUNCE_BYTES));
+        SAB_CUDA_TRY(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
+    }
+    return SAB_OK;
+}
+// host -> device on c->stream; returns with the copy ENQUEUED (pinned source) or COMPLETE (pageable source)
+int sab_copy_h2d(SabContext* c, void* d_dst, const void* h_src, size_t bytes) {
+    if (!bytes) return SAB_OK;
+    if (!sab_is_pageable(h_src)) {
+        SAB_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return SAB_OK;
+    }
+    SAB_TRY(sab_bounce_init(c));
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i) {
+        const int b = i & 1;
+        const size_t len = bytes - off < SAB_BOUNCE_BYTES ? bytes - off : SAB_BOUNCE_BYTES;
+        if (i >= 2) SAB_CUDA_TRY(cudaEventSynchronize(c->bounce_ev[b]));  // the DMA out of this buffer has finished
+        sab_parallel_memcpy(c->bounce[b], (const char*)h_src + off, len);
+        SAB_CUDA_TRY(cudaMemcpyAsync((char*)d_dst + off, c->bounce[b], len, cudaMemcpyHostToDevice, c->stream));
+        SAB_CUDA_TRY(cudaEventRecord(c->bounce_ev[b], c->stream));
+        off += len;
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SAB_OK;
+}
+// device -> host; everything enqueued on c->stream before the call is waited for; returns with the data in place
+int sab_copy_d2h(SabContext* c, void* h_dst, const void* d_src, size_t bytes) {
+    if (!bytes) return SAB_OK;
+    if (!sab_is_pageable(h_dst)) {
+        SAB_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return SAB_OK;
+    }
+    SAB_TRY(sab_bounce_init(c));
+    const size_t nchunks = (bytes + SAB_BOUNCE_BYTES - 1) / SAB_BOUNCE_BYTES;
+    auto issue = [&](size_t i) -> int {
+        const size_t off = i * SAB_BOUNCE_BYTES;
+        const size_t len = bytes - off < SAB_BOUNCE_BYTES ? bytes - off : SAB_BOUNCE_BYTES;
+        SAB_CUDA_TRY(cudaMemcpyAsync(c->bounce[i & 1], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, c->stream));
+        SAB_CUDA_TRY(cudaEventRecord(c->bounce_ev[i & 1], c->stream));
+        return SAB_OK;
+    };
+    SAB_TRY(issue(0));
+    for (size_t i = 0; i < nchunks; ++i) {
+        if (i + 1 < nchunks) SAB_TRY(issue(i + 1));  // its buffer was emptied by the memcpy of chunk i-1
+        SAB_CUDA_TRY(cudaEventSynchronize(c->bounce_ev[i & 1]));
+        const size_t off = i * SAB_BOUNCE_BYTES;
+        const size_t len = bytes - off < SAB_BOUNCE_BYTES ? bytes - off : SAB_BOUNCE_BYTES;
+        sab_parallel_memcpy((char*)h_dst + off, c->bounce[i & 1], len);
+    }
+    return SAB_OK;
+}
+
 static double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -292,7 +402,7 @@ static int32_t saca_host(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* b
     c->want_bkt = bkt ? d_bkt : nullptr;
     c->bkt_add_one = 1;
     double t0 = now_ms();
-    if (n) SAB_CUDA_TRY(cudaMemcpyAsync(d_s, s, n, cudaMemcpyHostToDevice, c->stream));
+    SAB_TRY(sab_copy_h2d(c, d_s, s, n));
     SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
     double t1 = now_ms();
     int rc = run_device(c, d_s, n, d_sa);
@@ -306,8 +416,7 @@ static int32_t saca_host(const uint8_t* s, uint64_t n, uint32_t* sa, uint32_t* b
                 SAB_CUDA_TRY(cudaMemcpyAsync(bkt, d_bkt, (size_t)SAB200_BKT_LEN * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
             }
         }
-        SAB_CUDA_TRY(cudaMemcpyAsync(sa, d_sa, (n + 1) * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
-        SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        SAB_TRY(sab_copy_d2h(c, sa, d_sa, (n + 1) * sizeof(u32)));
         c->stats.h2d_ms = t1 - t0;
         c->stats.d2h_ms = now_ms() - t2;
     }

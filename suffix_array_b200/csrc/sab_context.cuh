@@ -69,6 +69,8 @@ struct SabContext {
     size_t arena_bytes = 0;
     size_t arena_used = 0;
     size_t arena_want_seen = 0;
+    void* bounce[2] = {nullptr, nullptr};        // pinned bounce buffers for pageable caller memory (sab_copy_*)
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     u32* want_bkt = nullptr;     // device buffer for the fused bucket table of the running construction (or null)
     u32 bkt_add_one = 1;  // request the arena was last sized for (it may have been capped by the free memory)
     // profiling
@@ -97,6 +99,8 @@ static inline T* sab_arena_take(SabContext* c, size_t count) {
 }
 
 cudaEvent_t sab_event_get(SabContext* c);
+int sab_copy_h2d(SabContext* c, void* d_dst, const void* h_src, size_t bytes);
+int sab_copy_d2h(SabContext* c, void* h_dst, const void* d_src, size_t bytes);
 void sab_prof_begin(SabContext* c, int kind);
 void sab_prof_end(SabContext* c);
 void sab_prof_collect(SabContext* c);

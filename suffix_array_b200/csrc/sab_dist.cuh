@@ -1257,8 +1257,8 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
         // mapped (the lazy look-ups of the peer-to-peer rounds read the owner's text)
         u8* t = A.bot<u8>((size_t)shard_len + 64);
         SAB_ARENA_CHECK(A);
-        if (shard_len)
-            SAB_CUDA_TRY(cudaMemcpyAsync(t, shard, shard_len, shard_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        if (shard_len && shard_on_device) SAB_CUDA_TRY(cudaMemcpyAsync(t, shard, shard_len, cudaMemcpyDeviceToDevice, st));
+        else if (shard_len) SAB_TRY(sab_copy_h2d(c, t, shard, shard_len));
         d_text = t;
     }
     cudaEventRecord(e1, st);
@@ -1288,8 +1288,7 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
     cudaEventRecord(e2, st);
     if (h_bkt_part) SAB_CUDA_TRY(cudaMemcpyAsync(h_bkt_part, d_bkt, (size_t)SAB200_BKT_LEN * sizeof(u32), cudaMemcpyDeviceToHost, st));
     if (host_out_base) {
-        if (res.slice_len)
-            SAB_CUDA_TRY(cudaMemcpyAsync(host_out_base + res.sa_off, res.d_slice, res.slice_len * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        if (res.slice_len) SAB_TRY(sab_copy_d2h(c, host_out_base + res.sa_off, res.d_slice, res.slice_len * sizeof(u32)));
         if (cm->rank == 0) {
             c->h_small[32] = (u32)n;
             memcpy(host_out_base, c->h_small + 32, sizeof(u32));  // sa[0] = n (src/saca.rs:13)
@@ -1300,9 +1299,10 @@ static int sab_sharded_run(sab200_comm* cm, const u8* shard, u64 shard_len, u64 
                           (unsigned long long)out_cap);
             return SAB_ERR_ARGS;
         }
-        if (res.slice_len)
-            SAB_CUDA_TRY(cudaMemcpyAsync(out, res.d_slice, res.slice_len * sizeof(u32),
-                                         out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (res.slice_len && out_on_device)
+            SAB_CUDA_TRY(cudaMemcpyAsync(out, res.d_slice, res.slice_len * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        else if (res.slice_len)
+            SAB_TRY(sab_copy_d2h(c, out, res.d_slice, res.slice_len * sizeof(u32)));
     }
     cudaEventRecord(e3, st);
     SAB_CUDA_TRY(cudaStreamSynchronize(st));

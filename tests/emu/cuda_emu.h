@@ -215,7 +215,7 @@ typedef struct emu_stream* cudaStream_t;
 typedef struct emu_event { double t; }* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostRegisterDefault = 0, cudaEventDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostRegisterDefault = 0, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 struct cudaDeviceProp {
     char name[256];
     int multiProcessorCount;
