@@ -16,8 +16,11 @@ struct PassShape;
 #ifndef SAB_PASS_THREADS
 #define SAB_PASS_THREADS 256
 #endif
+// 18 items: 4608-record tiles (longer per-bin runs, fewer partial sectors), 64 KB of shared memory, still
+// 3 CTAs/SM and 80 registers (8 bytes of spill).  Measured on the 1 GiB text: 14 items 3263 GB/s, 16: 3401,
+// 18: 3547, 20: 3217 (profiles/r02_ab_radix_variants*.txt).
 #ifndef SAB_PASS_ITEMS
-#define SAB_PASS_ITEMS 16
+#define SAB_PASS_ITEMS 18
 #endif
 template <>
 struct PassShape<u64> {

@@ -116,13 +116,14 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
 
 def test_emu_radix_sort_direct(emu_lib):
     """The LSD radix sort on its own (through sab200_sort_pairs_device): stable order of (key, payload) pairs
-    against numpy for sizes around the tile (4096) and look-back group (8 tiles) limits and for skewed,
+    against numpy for sizes around the tile (256 threads x 18 items = 4608) and look-back group (8 tiles) limits and for skewed,
     constant and wide digits -- the two-level look-back sees complete, partial and single groups."""
     import ctypes as C
     L = emu_lib
     rng = np.random.default_rng(123)
     cases = []
-    for n in (1, 31, 4095, 4096, 4097, 8 * 4096, 8 * 4096 + 1, 9 * 4096 - 1, 70000, 17 * 4096):
+    T = 4608  # SAB_PASS_THREADS * SAB_PASS_ITEMS (csrc/sab_sort.cuh)
+    for n in (1, 31, 4095, 4096, 4097, T - 1, T, T + 1, 8 * T, 8 * T + 1, 9 * T - 1, 70000, 17 * T):
         cases.append((n, 64, rng.integers(0, 2 ** 63, n, dtype=np.int64).astype(np.uint64) * np.uint64(2)
                       + rng.integers(0, 2, n, dtype=np.int64).astype(np.uint64)))
     cases.append((50000, 17, rng.integers(0, 2 ** 17, 50000, dtype=np.int64).astype(np.uint64)))          # 3 passes, top one partial
