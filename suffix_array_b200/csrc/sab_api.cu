@@ -227,7 +227,7 @@ static void sab_parallel_memcpy(void* dst, const void* src, size_t bytes) {
         return;
     }
     std::vector<std::thread> th;
-    const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
+    const size_t per = (((bytes + (size_t)T - 1) / (size_t)T) + 4095) & ~(size_t)4095;  // T * per >= bytes
     for (int i = 1; i < T; ++i) {
         const size_t lo = (size_t)i * per;
         if (lo >= bytes) break;
