@@ -213,6 +213,13 @@ typedef struct sab200_dist_stats {
  * (d_k0, d_v0) / (d_k1, d_v1) that holds the result, < 0 on error. */
 int32_t sab200_sort_pairs_device(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
                                  int32_t key_bits, int32_t device);
+/* Building block, exported for tests and tools: the in-group sort of a doubling round (csrc/sab_group_sort.cuh).
+ * The `count` records of (d_k0, d_v0) are grouped by the high 32 bits of their keys (equal high words are
+ * contiguous; `ascending` != 0: the groups also arrive in ascending order) and are ordered by the full key inside
+ * every group; records with equal keys end up in unspecified order.  Device memory on `device`.  Returns the buffer
+ * pair holding the result (always 1), < 0 on error; *nbig_out = records that took the radix-sort path. */
+int32_t sab200_group_sort_device(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
+                                 int32_t key_bits, int32_t ascending, int32_t device, uint64_t* nbig_out);
 /* Copies `bytes` from the library's device arena on `device` (a d_slice pointer) into host memory. */
 int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device);
 /* counters of the last sharded construction on `comm` */

@@ -144,6 +144,7 @@ def _bind(L):
         "sab200_saca_sharded": ([vp, vp, u64, u64, i32, vp, u64, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp)], i32),
         "sab200_copy_from_device": ([vp, vp, u64, i32], i32),
         "sab200_sort_pairs_device": ([vp, vp, vp, vp, u64, i32, i32], i32),
+        "sab200_group_sort_device": ([vp, vp, vp, vp, u64, i32, i32, i32, C.POINTER(u64)], i32),
         "sab200_comm_stats": ([vp, C.POINTER(DistStats)], i32),
         "sab200_multi_stats": ([i32, C.POINTER(DistStats)], i32),
     }

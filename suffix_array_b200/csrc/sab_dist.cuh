@@ -1345,6 +1345,44 @@ extern "C" int32_t sab200_sort_pairs_device(uint64_t* d_k0, uint64_t* d_k1, uint
     return buf.cur;
 }
 
+extern "C" int32_t sab200_group_sort_device(uint64_t* d_k0, uint64_t* d_k1, uint32_t* d_v0, uint32_t* d_v1, uint64_t count,
+                                            int32_t key_bits, int32_t ascending, int32_t device, uint64_t* nbig_out) {
+    SabContext* c = sab_get_context(device);
+    if (!c) return SAB_ERR_CUDA;
+    if (key_bits < 32 || key_bits > 64 || count > 0xfffffff0ull) return SAB_ERR_ARGS;
+    if (nbig_out) *nbig_out = 0;
+    if (count == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    SAB_CUDA_TRY(cudaSetDevice(c->device));
+    const u64 cap = sab_align_up((size_t)count * 2 + 64, 64);  // room for every record, and for the position sort
+    SAB_TRY(sab_arena_reserve(c, (size_t)cap * (2 * 8 + 3 * 4) + 8 * 256));
+    c->arena_used = 0;
+    GroupSortSpare sp;
+    sp.k[0] = sab_arena_take<u64>(c, cap);
+    sp.k[1] = sab_arena_take<u64>(c, cap);
+    sp.v[0] = sab_arena_take<u32>(c, cap);
+    sp.v[1] = sab_arena_take<u32>(c, cap);
+    sp.pos = sab_arena_take<u32>(c, cap);
+    sp.cap = cap;
+    SortBuffers<u64> sb;
+    sb.k[0] = d_k0;
+    sb.k[1] = d_k1;
+    sb.v[0] = d_v0;
+    sb.v[1] = d_v1;
+    sb.cur = 0;
+    u32 passes = 0;
+    u64 nbig = 0;
+    const int rc = sab_group_sort(c, sb, count, key_bits, sp, &passes, &nbig, ascending != 0);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        sab_set_error("group sort: the records of large groups did not fit the spare buffers");
+        return SAB_ERR_INTERNAL;
+    }
+    SAB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (nbig_out) *nbig_out = nbig;
+    return sb.cur;
+}
+
 extern "C" int32_t sab200_copy_from_device(void* dst, const void* d_src, uint64_t bytes, int32_t device) {
     if (!dst || !d_src) return bytes ? SAB_ERR_ARGS : SAB_OK;
     SabContext* c = sab_get_context(device);

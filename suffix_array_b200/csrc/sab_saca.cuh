@@ -26,6 +26,12 @@
 #include "sab_scan_kernels.cuh"
 #include "sab_group_sort.cuh"
 
+// The bucket directory of the lazy inverse suffix array has 2^(ceil(log2 n) - SAB_DIR_SHIFT) entries (at most
+// 2^28): ~2^SAB_DIR_SHIFT sorted keys per entry for the gallop + bisect that follows the jump.
+#ifndef SAB_DIR_SHIFT
+#define SAB_DIR_SHIFT 4
+#endif
+
 #define SAB_RANK_EMPTY 0xffffffffu
 #define SAB_PAD(o) ((o) + ((o) >> 5))  // shared-memory padding, one word per 32; NB: evaluates its argument twice
 // 1: the records of a round are ordered inside their groups by sab_group_sort (one sweep + a radix sort
@@ -407,7 +413,7 @@ static int sab_fused_buckets(SabContext* c, const u8* d_text, u64 n, const u64* 
 // bytes of arena needed for a text of n bytes (excluding text and sa, which the caller provides)
 static inline size_t sab_saca_workspace_bytes(u64 n) {
     const size_t N = (size_t)n + 8;
-    int dir_bits = sab_ceil_log2_u64(n) - 4;
+    int dir_bits = sab_ceil_log2_u64(n) - SAB_DIR_SHIFT;
     if (dir_bits > 28) dir_bits = 28;
     if (dir_bits < 1) dir_bits = 1;
     return 2 * sab_align_up(N * 8, 256) + 3 * sab_align_up(N * 4, 256) + sab_align_up((N + 1) * 4, 256) +
@@ -490,7 +496,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     const u32* sortedI = sa_written ? d_sa + 1 : buf.v[buf.cur];
     u64* free_keys = buf.k[buf.cur ^ 1];
     u32* act_idx = buf.v[buf.cur ^ 1];
-    int dir_bits = sab_ceil_log2_u64(n) - 4;
+    int dir_bits = sab_ceil_log2_u64(n) - SAB_DIR_SHIFT;
     if (dir_bits > 28) dir_bits = 28;
     if (dir_bits > key_bits) dir_bits = key_bits;
     if (dir_bits < 1) dir_bits = 1;
@@ -564,9 +570,10 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     bool group_sort_on = SAB_GROUP_SORT != 0;
     // The active list leaves init_ranks ascending in r1.  A round of the split filter parks the unsplit
     // groups in front of the re-ranked ones, so the next list is two ascending runs: groups stay contiguous
-    // (all the scan kernels need) but the list is no longer monotone -- and sab_group_sort returns the
-    // radix-sorted records of large groups to their positions in LIST order, which needs a monotone list.
+    // (all the scan kernels need) but the list is no longer monotone -- sab_group_sort is told, because it
+    // returns the radix-sorted records of large groups to their positions in the order of their groups.
     bool list_sorted = true;
+    int gs_pause = 0;  // rounds the in-group sort sits out after its large-group records did not fit
     while (m > 0) {
         ++round;
         if (round >= SAB_MAX_ROUNDS || h > n) {
@@ -612,7 +619,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             // 5d. small groups are ordered in one sweep; the spare buffers for the records of big groups are
             // the unused tails of the round buffers (keys, payloads) and of r1buf (positions)
             int sorted = 0;
-            if (group_sort_on && list_sorted) {
+            if (group_sort_on) {
                 const u64 used = sab_align_up(n_sort, 64);
                 const u64 cap_keys = key_cap > used ? key_cap - used : 0;
                 const u64 cap_vals = n + 8 > n_stay + used ? n + 8 - n_stay - used : 0;
@@ -623,11 +630,17 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
                 sp.v[1] = sb.v[1] + used;
                 sp.pos = r1buf + n_stay;
                 sp.cap = cap_keys < cap_vals ? cap_keys : cap_vals;
-                if (sp.cap * 8 >= n_sort) {
+                // the sweep is tried whenever there is any spare room: it reports how many records belong to
+                // large groups even when they do not fit (then the round takes the radix sort and the sweep
+                // pauses for two rounds -- the list, and with it the need for room, only shrinks)
+                if (sp.cap >= 64 && gs_pause == 0) {
                     u64 nbig = 0;
-                    sorted = sab_group_sort(c, sb, n_sort, 32 + rank_bits, sp, &S.passes[round], &nbig);
+                    sorted = sab_group_sort(c, sb, n_sort, 32 + rank_bits, sp, &S.passes[round], &nbig, list_sorted);
                     if (sorted < 0) return sorted;
                     if (nbig * 2 > n_sort) group_sort_on = false;  // mostly large groups: the sweep does not pay
+                    else if (!sorted) gs_pause = 2;
+                } else if (gs_pause > 0) {
+                    --gs_pause;
                 }
             }
             if (!sorted) SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));

@@ -224,3 +224,80 @@ def random_text(rng):
         return np.concatenate([a, b, a[:n // 5]])
     base = gen.repetitive(max(n, 100), block=int(rng.integers(50, 1500)), mut_rate=float(rng.choice([1e-3, 1e-2])))
     return np.concatenate([base, gen.dna_like(max(n // 3, 10)), base[:n // 2]])
+
+
+def grouped_records(rng, sizes, r2_values, ascending=True):
+    """A round's records: groups of the given sizes, contiguous, keyed (r1 << 32) | r2 with r1 = the position a
+    sorted suffix array would give the group head; r2 drawn from `r2_values` distinct values (many ties)."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    heads = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) * np.uint64(3) + np.uint64(1)
+    order = np.arange(sizes.size)
+    if not ascending:  # two ascending runs, as a split-filter round leaves them
+        cut = sizes.size // 3
+        order = np.concatenate([order[cut:], order[:cut]])
+    r1 = np.repeat(heads[order], sizes[order])
+    m = int(sizes.sum())
+    r2 = rng.integers(0, max(1, r2_values), m, dtype=np.int64).astype(np.uint64)
+    if r2_values > 4:
+        r2 = r2 * np.uint64(977) + np.uint64(5)
+    keys = (r1 << np.uint64(32)) | r2
+    vals = rng.permutation(m).astype(np.uint32)
+    return keys, vals
+
+
+def check_group_sort(lib, keys, vals, ascending=True, to_device=None, from_device=None):
+    """sab200_group_sort_device against numpy: keys ordered inside every group, the (key, payload) pairs of a
+    group preserved as a multiset.  to_device / from_device move arrays for the GPU build (the emulator's
+    'device' memory is host memory)."""
+    import ctypes as C
+    m = keys.size
+    hold = []
+
+    def dev(a):
+        if to_device is None:
+            b = a.copy()
+            hold.append(b)
+            return b, b.ctypes.data
+        t = to_device(a)
+        hold.append(t)
+        return t, t.data_ptr()
+
+    k0, pk0 = dev(keys)
+    k1, pk1 = dev(np.zeros(m, dtype=np.uint64))
+    v0, pv0 = dev(vals)
+    v1, pv1 = dev(np.zeros(m, dtype=np.uint32))
+    nbig = C.c_uint64()
+    which = lib.sab200_group_sort_device(pk0, pk1, pv0, pv1, m, 64, 1 if ascending else 0, 0, C.byref(nbig))
+    assert which == (1 if m else 0), (which, lib.sab200_last_error())
+    if m == 0:
+        return 0
+    ok = k1 if from_device is None else from_device(k1)
+    ov = v1 if from_device is None else from_device(v1)
+    gid = np.cumsum(np.concatenate([[0], (keys[1:] >> np.uint64(32)) != (keys[:-1] >> np.uint64(32))]))
+    exp_order = np.lexsort((vals, keys, gid))
+    assert np.array_equal(ok, keys[exp_order]), "keys not ordered inside their groups"
+    got_order = np.lexsort((ov, ok, gid))
+    assert np.array_equal(ov[got_order], vals[exp_order]), "payloads do not follow their keys"
+    return int(nbig.value)
+
+
+def group_sort_cases(rng):
+    """(sizes, distinct second ranks, ascending) around every limit of group_sort_kernel: counting rank <= 32,
+    warp sort 64 / 128 / 256 / 512, the radix path beyond; groups cut by the 2048-record tile borders."""
+    cases = []
+    for s in (1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 512, 513, 700, 2048, 2049, 5000):
+        cases.append(([s] * max(3, 6000 // s), 1 << 20, True))
+        cases.append(([s] * max(3, 4200 // s) + [1, 2, 3], 3, True))
+    cases.append((rng.integers(1, 40, 900).tolist(), 50, True))
+    cases.append((rng.integers(1, 600, 60).tolist(), 7, True))
+    cases.append((rng.integers(200, 300, 70).tolist(), 1 << 16, True))
+    cases.append((rng.integers(1, 1100, 40).tolist(), 1 << 16, True))
+    cases.append(([2047, 1, 2048, 1, 511, 1537, 512, 1536, 513, 1535, 2047 + 512, 1, 2046, 514], 5, True))
+    cases.append(([1536, 1024, 1024, 512, 3000, 32, 33, 2015, 33], 1 << 10, True))
+    cases.append(([256] * 100, 2, True))
+    cases.append(([1], 1, True))
+    cases.append(([5], 1, True))
+    cases.append(([], 1, True))
+    for c in list(cases[-9:-3]) + [cases[20], cases[30]]:
+        cases.append((c[0], c[1], False))
+    return cases

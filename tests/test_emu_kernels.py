@@ -93,11 +93,11 @@ def SuffixArrayBanana():
 
 def test_emu_group_sort_boundaries(emu_backend, oracle):
     """Rounds whose groups sit right at the limits of group_sort_kernel: a random block repeated r times gives
-    groups of r records (r = 32: ordered in shared memory, r = 33: radix path), lists longer than one
-    2048-record tile (groups cut by tile borders), and mixtures of both kinds."""
+    groups of r records (r = 32: counting rank, r = 33: warp sort, r = 600: radix path), lists longer than one
+    2048-record tile (groups cut by tile borders), and mixtures of the kinds."""
     from suffix_array_b200 import _lib, gen
     rng = np.random.default_rng(77)
-    for r, blk in ((31, 97), (32, 90), (33, 90), (34, 61), (2, 1500), (3, 1100)):
+    for r, blk in ((31, 97), (32, 90), (33, 90), (34, 61), (2, 1500), (3, 1100), (130, 40), (600, 9)):
         block = rng.integers(0, 4, blk, dtype=np.uint8)
         t = np.concatenate([np.tile(block, r), rng.integers(0, 4, 50, dtype=np.uint8)])
         pc.check_construction(oracle, t)
@@ -107,7 +107,7 @@ def test_emu_group_sort_boundaries(emu_backend, oracle):
     # must then go through the full radix sort (regression: they were returned to positions of other groups)
     pc.check_construction(oracle, gen.repetitive(9518, block=2180, mut_rate=0.01))
     # small and large groups interleaved in one list
-    a = np.tile(rng.integers(0, 4, 70, dtype=np.uint8), 40)
+    a = np.tile(rng.integers(0, 4, 7, dtype=np.uint8), 700)
     b = np.tile(rng.integers(0, 4, 400, dtype=np.uint8), 3)
     pc.check_construction(oracle, np.concatenate([a, rng.integers(0, 4, 3000, dtype=np.uint8), b]))
     st = _lib.last_stats()
@@ -211,3 +211,18 @@ print("ok")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                          env=dict(os.environ, SAB_FORCE_STAGED="1", SAB_COPY_THREADS="6"))
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_emu_group_sort_direct(emu_lib):
+    """group_sort_kernel on its own (through sab200_group_sort_device) against numpy: every size class, groups cut
+    by tile borders (completed by the tile that owns the head), lists that are not ascending in r1."""
+    rng = np.random.default_rng(99)
+    seen_big = seen_none = 0
+    for sizes, r2v, asc in pc.group_sort_cases(rng):
+        keys, vals = pc.grouped_records(rng, sizes, r2v, asc)
+        nbig = pc.check_group_sort(emu_lib, keys, vals, asc)
+        exp_big = int(sum(s for s in sizes if s > 512))
+        assert nbig == exp_big, (sizes[:8], nbig, exp_big)
+        seen_big += nbig > 0
+        seen_none += nbig == 0
+    assert seen_big and seen_none

@@ -169,6 +169,32 @@ def test_filter_and_group_sort_rounds(gpu_lib, oracle):
         assert SuffixArray.from_parts(s, sa.sa) is not None
 
 
+def test_group_sort_direct(gpu_lib):
+    """group_sort_kernel on its own (sab200_group_sort_device) against numpy, device buffers through torch: every
+    size class (counting rank <= 32, warp sort <= 512, radix path beyond), groups cut by tile borders, lists
+    that are not ascending; plus a 32 Mi-record list of ~256-record groups (the shape of BASELINE configs[2])."""
+    import torch
+    rng = np.random.default_rng(99)
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32)).cuda()
+
+    def from_dev(t):
+        a = t.cpu().numpy()
+        return a.view(np.uint64) if a.dtype == np.int64 else a.view(np.uint32)
+
+    for sizes, r2v, asc in pc.group_sort_cases(rng):
+        keys, vals = pc.grouped_records(rng, sizes, r2v, asc)
+        nbig = pc.check_group_sort(gpu_lib, keys, vals, asc, to_dev, from_dev)
+        assert nbig == int(sum(x for x in sizes if x > 512)), (sizes[:8], nbig)
+    sizes = rng.integers(200, 300, (32 << 20) // 250)
+    keys, vals = pc.grouped_records(rng, sizes, 3, True)
+    assert pc.check_group_sort(gpu_lib, keys, vals, True, to_dev, from_dev) == 0
+    sizes = rng.integers(1, 1200, (8 << 20) // 600)
+    keys, vals = pc.grouped_records(rng, sizes, 1 << 20, False)
+    assert pc.check_group_sort(gpu_lib, keys, vals, False, to_dev, from_dev) == int(sizes[sizes > 512].sum())
+
+
 def test_c1_uniform_64mib(gpu_lib, oracle):
     # BASELINE.json configs[0] at full size: linear-time verifiers on CPU and GPU
     s = gen.uniform_bytes(64 << 20)
