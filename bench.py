@@ -21,6 +21,7 @@ text of configs[3]) and the batched search of configs[4] sharded over N replicas
                  oracle sufcheck on the CPU for the 1 GiB text)
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -242,11 +243,15 @@ def bench_search(L, _lib, torch, dev, text, sa, n, ngpus, npat, sample=1_000_000
     from oracle import oracle
     bkt = np.empty(_lib.BKT_LEN, dtype=np.uint32)
     _lib.check(L.sab200_enable_buckets(text.ctypes.data, n, bkt.ctypes.data), "sab200_enable_buckets")
+    t0 = time.perf_counter()
     ix = L.sab200_index_create(text.ctypes.data, n, sa.ctypes.data, n + 1, bkt.ctypes.data, ngpus)
+    create_ms = (time.perf_counter() - t0) * 1e3
     if not ix:
         return {"error": L.sab200_last_error().decode()}
     peak, _ = hbm_peak()
-    out = {"patterns": npat, "len": "8..64", "replicas": ngpus, "buckets": True}
+    out = {"patterns": npat, "len": "8..64", "replicas": ngpus, "buckets": True,
+           "index_create_ms": round(create_ms, 1),
+           "index_create_note": "upload of text + suffix array + bucket table from pageable memory and the prefix directory, per replica; not in the timed region"}
     for name, alphabet in (("alphabet_hybrid", None), ("raw_byte_hybrid", np.arange(256, dtype=np.uint8))):
         pats, offs = gen.patterns(text, npat, alphabet=alphabet)
         _, hp = pinned(pats.size + 64, torch.uint8)
@@ -275,16 +280,34 @@ def bench_search(L, _lib, torch, dev, text, sa, n, ngpus, npat, sample=1_000_000
                 t0 = time.perf_counter()
                 _lib.check(L.sab200_search_all_batch_device(ix, d_p.data_ptr(), d_o.data_ptr(), npat, d_lo.data_ptr(), d_hi.data_ptr()), "search_dev")
                 best = min(best, time.perf_counter() - t0)
-            algo, sector, probes = search_bytes(bkt, pats, offs, n)
+            ref_algo, ref_sector, ref_probes = search_bytes(bkt, pats, offs, n)
+            # probes the kernel really makes (it starts from the prefix directory of the resident index, not from the
+            # whole bucket): counted by the kernel itself in one extra, untimed pass
+            p0 = L.sab200_index_probes(ix, 1)
+            _lib.check(L.sab200_search_all_batch_device(ix, d_p.data_ptr(), d_o.data_ptr(), npat, d_lo.data_ptr(), d_hi.data_ptr()), "search_dev")
+            probes = int(L.sab200_index_probes(ix, 0) - p0)
+            lens = (offs[1:] - offs[:-1]).astype(np.int64)
+            per_probe = float((4 + np.minimum(lens, 32)).mean())
+            per_probe_sector = float((32 * (1 + (lens + 31) // 32)).mean())
+            algo = int(probes * per_probe + 16 * npat)        # + two bucket and two directory entries per query
+            sector = int(probes * per_probe_sector + 3 * 32 * npat)
             rec.update({"queries_per_s_kernel": round(npat / best, 1), "kernel_ms": round(best * 1e3, 3),
                         "device_equals_host": bool(np.array_equal(d_lo.cpu().numpy().view(np.uint32), lo)),
                         "roofline": {"bound": "hbm (dependent random 32-byte sectors)", "kernel": "search_kernel<8, search_all>",
-                                     "probes": probes, "algorithmic_bytes": algo, "sector_bytes": sector,
+                                     "probes": probes, "probes_per_query": round(probes / npat, 2),
+                                     "algorithmic_bytes": algo, "sector_bytes": sector,
                                      "achieved": round(algo / 1e9 / best, 1), "achieved_sector": round(sector / 1e9 / best, 1),
                                      "peak": peak, "unit": "GB/s", "frac": round(algo / 1e9 / best / peak, 4),
                                      "frac_sector": round(sector / 1e9 / best / peak, 4),
-                                     "formula": "SURVEY.md 8d: 2*ceil(log2(bucket))*(4+min(|pat|,32)) B per query; "
-                                                "sector-level 32 B*(1+ceil(|pat|/32)) per probe"}})
+                                     "formula": "probes counted by the kernel * (4 + min(|pat|,32)) B (SURVEY.md 8d per-probe bytes) "
+                                                "+ 16 B of bucket / directory entries per query; sector-level 32 B*(1+ceil(|pat|/32)) "
+                                                "per probe + 3 sectors per query",
+                                     "reference_bisection": {"probes": ref_probes, "algorithmic_bytes": ref_algo, "sector_bytes": ref_sector,
+                                                             "note": "SURVEY.md 8d as written: 2*ceil(log2(bucket)) probes per query -- what "
+                                                                     "bisecting the whole two-byte bucket (src/sa.rs:181-201) would read"}}})
+            sg, dp = ctypes.c_uint32(), ctypes.c_uint32()
+            ent = int(L.sab200_index_directory(ix, ctypes.byref(sg), ctypes.byref(dp)))
+            out["prefix_directory"] = {"entries": ent, "base": int(sg.value), "depth": int(dp.value)}
             del d_p, d_o, d_lo, d_hi
         ns = min(sample, npat)
         so = offs[:ns + 1]

@@ -136,6 +136,16 @@ int32_t sab200_search_lcp_batch(sab200_index* ix, const uint8_t* pats, const uin
 int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_t* d_pats, const uint64_t* d_offs, uint64_t np,
                                        uint32_t* d_lo, uint32_t* d_hi);
 
+/* Introspection of a resident index (bench and tests).  sab200_index_create also builds a PREFIX DIRECTORY over the
+ * resident text and suffix array (csrc/sab_search.cuh: number of suffixes below every code of `depth` leading symbols
+ * in base `sigma`), from which search_all / contains start their bisection instead of from the whole two-byte
+ * bucket; the answers are unchanged.  SAB_SEARCH_DIR=0 in the environment leaves it out.
+ * sab200_index_directory: number of entries (0 = none), base and depth of replica 0.
+ * sab200_index_probes: switches the counting of suffix comparisons in search_all on / off (one atomic per pattern:
+ * not for timed runs) and returns the count accumulated so far over all replicas. */
+uint64_t sab200_index_directory(sab200_index* ix, uint32_t* sigma, uint32_t* depth);
+uint64_t sab200_index_probes(sab200_index* ix, int32_t count_on);
+
 /* ---- pack serialisation --------------------------------------------------------------------
  * Replaces PackedSuffixArray::from_sa + dump_bytes and load_bytes + into_sa (src/packed_sa.rs:17-88,
  * 99-124; behind SuffixArray::dump* / load*, src/sa.rs:256-361, feature "pack"): bincode little-endian

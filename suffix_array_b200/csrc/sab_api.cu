@@ -556,6 +556,12 @@ struct SabReplica {
     u8* d_text = nullptr;
     u32* d_sa = nullptr;
     u32* d_bkt = nullptr;
+    // prefix directory (sab_search.cuh PrefixDir): built here, never leaves the library
+    u32* d_pdir = nullptr;
+    u16* d_plut = nullptr;
+    unsigned long long* d_probes = nullptr;
+    PrefixDir pd;
+    cudaStream_t stream2 = nullptr;  // second stream: the copies of one chunk of patterns run under the kernel of another
     // query scratch (grow-only)
     u8* d_pats = nullptr;
     size_t pats_cap = 0;
@@ -567,6 +573,7 @@ struct SabReplica {
 struct sab200_index {
     u64 n = 0;
     bool has_bkt = false;
+    bool count_probes = false;
     std::vector<SabReplica> rep;
     std::mutex mu;
 };
@@ -577,11 +584,72 @@ static void replica_free(SabReplica& r) {
     cudaFree(r.d_text);
     cudaFree(r.d_sa);
     cudaFree(r.d_bkt);
+    cudaFree(r.d_pdir);
+    cudaFree(r.d_plut);
+    cudaFree(r.d_probes);
     cudaFree(r.d_pats);
     cudaFree(r.d_offs);
     cudaFree(r.d_out0);
     cudaFree(r.d_out1);
+    if (r.stream2) cudaStreamDestroy(r.stream2);
     r = SabReplica();
+}
+
+// The prefix directory over the resident text and suffix array: alphabet from a byte histogram on the device, depth
+// = the most symbols whose codes number at most n / 8 (between 2^16 and 2^27 entries), one sweep over the suffix
+// array.  Running out of memory for it is not an error: the queries then bisect the whole bucket.
+static int replica_build_prefix_dir(SabReplica& r, u64 n) {
+    SabContext* c = r.ctx;
+    cudaStream_t st = c->stream;
+    std::lock_guard<std::mutex> lk(c->mu);
+    u32* d_hist = c->d_counters + 16;
+    SAB_CUDA_TRY(cudaMemsetAsync(d_hist, 0, 256 * sizeof(u32), st));
+    u64 blocks = div_up64(n, 256 * 64);
+    if (blocks > (u64)c->sm_count * 8) blocks = (u64)c->sm_count * 8;
+    SAB_LAUNCH(alphabet_hist_kernel, (unsigned)blocks, 256, 0, st, (const u8*)r.d_text, n, d_hist);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaMemcpyAsync(c->h_small + 64, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    u16 lut[256];
+    u32 sigma = 0;
+    for (int ch = 0; ch < 256; ++ch) {
+        const bool present = c->h_small[64 + ch] != 0;
+        lut[ch] = (u16)(sigma | (present ? 0x8000u : 0u));
+        if (present) ++sigma;
+    }
+    const u32 base = sigma < 2 ? 2 : sigma;
+    u64 limit = n / 8;
+    if (limit < (1ull << 16)) limit = 1ull << 16;
+    if (limit > (1ull << 27)) limit = 1ull << 27;
+    u32 depth = 1;
+    u64 entries = base;
+    while (depth < SAB_PDIR_MAXD && entries * base <= limit) {
+        entries *= base;
+        ++depth;
+    }
+    if (cudaMalloc(&r.d_pdir, (entries + 1) * sizeof(u32)) != cudaSuccess) {
+        cudaGetLastError();
+        r.d_pdir = nullptr;
+        return SAB_OK;
+    }
+    SAB_CUDA_TRY(cudaMalloc(&r.d_plut, sizeof(lut)));
+    memcpy(c->h_small + 384, lut, sizeof(lut));  // pinned staging
+    SAB_CUDA_TRY(cudaMemcpyAsync(r.d_plut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
+    u64 fblocks = div_up64(entries + 1, 256 * 8);
+    if (fblocks > (u64)c->sm_count * 16) fblocks = (u64)c->sm_count * 16;
+    SAB_LAUNCH(fill_u32_kernel, (unsigned)fblocks, 256, 0, st, r.d_pdir, entries + 1, (u32)(n + 1));
+    SAB_LAUNCH_CHECK();
+    SAB_LAUNCH(prefix_dir_kernel, (unsigned)div_up64(n + 1, 256), 256, 0, st, (const u8*)r.d_text, n, (const u32*)r.d_sa, n + 1,
+               (const u16*)r.d_plut, base, depth, r.d_pdir);
+    SAB_LAUNCH_CHECK();
+    SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    r.pd.dir = r.d_pdir;
+    r.pd.lut = r.d_plut;
+    r.pd.sigma = base;
+    r.pd.depth = depth;
+    r.pd.pw[0] = 1;
+    for (u32 t = 1; t <= SAB_PDIR_MAXD; ++t) r.pd.pw[t] = t <= depth ? r.pd.pw[t - 1] * base : 0;
+    return SAB_OK;
 }
 
 static int replica_init(SabReplica& r, int device, const u8* s, u64 n, const u32* sa, const u32* bkt) {
@@ -600,6 +668,12 @@ static int replica_init(SabReplica& r, int device, const u8* s, u64 n, const u32
         SAB_CUDA_TRY(cudaMemcpyAsync(r.d_bkt, bkt, SAB_BKT_LEN * sizeof(u32), cudaMemcpyHostToDevice, st));
     }
     SAB_CUDA_TRY(cudaStreamSynchronize(st));
+    memset(&r.pd, 0, sizeof(r.pd));
+    SAB_CUDA_TRY(cudaStreamCreateWithFlags(&r.stream2, cudaStreamNonBlocking));
+    SAB_CUDA_TRY(cudaMalloc(&r.d_probes, sizeof(unsigned long long)));
+    SAB_CUDA_TRY(cudaMemsetAsync(r.d_probes, 0, sizeof(unsigned long long), st));
+    const char* off = getenv("SAB_SEARCH_DIR");
+    if (n > 0 && !(off && off[0] == '0')) SAB_TRY(replica_build_prefix_dir(r, n));
     return SAB_OK;
 }
 
@@ -640,8 +714,12 @@ extern "C" void sab200_index_destroy(sab200_index* ix) {
 }
 
 template <int MODE>
-static int launch_search(SabReplica& r, u64 n, const u8* d_pats_adj, const u64* d_offs, u64 np, u32* d_out0, u32* d_out1) {
+static int launch_search(SabReplica& r, u64 n, const u8* d_pats_adj, const u64* d_offs, u64 np, u32* d_out0, u32* d_out1,
+                         bool count_probes = false, cudaStream_t st = nullptr) {
+    if (!st) st = r.ctx->stream;
     SearchArgs a;
+    a.pd = r.pd;
+    a.probes = count_probes ? r.d_probes : nullptr;
     a.text = r.d_text;
     a.n = n;
     a.sa = r.d_sa;
@@ -652,12 +730,14 @@ static int launch_search(SabReplica& r, u64 n, const u8* d_pats_adj, const u64* 
     a.out0 = d_out0;
     a.out1 = d_out1;
     const u64 threads = np * SAB_SEARCH_G;
-    SAB_LAUNCH((search_kernel<SAB_SEARCH_G, MODE>), (unsigned)div_up64(threads, SAB_SEARCH_THREADS), SAB_SEARCH_THREADS, 0,
-               r.ctx->stream, a);
+    SAB_LAUNCH((search_kernel<SAB_SEARCH_G, MODE>), (unsigned)div_up64(threads, SAB_SEARCH_THREADS), SAB_SEARCH_THREADS, 0, st, a);
     SAB_LAUNCH_CHECK();
     return SAB_OK;
 }
 
+#ifndef SAB_SEARCH_CHUNK
+#define SAB_SEARCH_CHUNK (1ull << 20)  // patterns per pipelined chunk
+#endif
 static int replica_reserve(SabReplica& r, size_t pat_bytes, size_t np) {
     if (r.pats_cap < pat_bytes + 64) {
         cudaFree(r.d_pats);
@@ -668,7 +748,7 @@ static int replica_reserve(SabReplica& r, size_t pat_bytes, size_t np) {
         SAB_CUDA_TRY(cudaMemset(r.d_pats, 0, want));
         r.pats_cap = want;
     }
-    if (r.np_cap < np + 1) {
+    if (r.np_cap < np + np / SAB_SEARCH_CHUNK + 2) {  // every pipelined chunk keeps its own end offset
         cudaFree(r.d_offs);
         cudaFree(r.d_out0);
         cudaFree(r.d_out1);
@@ -707,24 +787,38 @@ static int search_batch(sab200_index* ix, int mode, const u8* pats, const u64* o
         const u64 b0 = offs[q0], b1 = offs[q1];
         const u64 cnt = q1 - q0;
         SAB_TRY(replica_reserve(r, (size_t)(b1 - b0), (size_t)cnt));
-        cudaStream_t st = r.ctx->stream;
-        if (b1 > b0) SAB_CUDA_TRY(cudaMemcpyAsync(r.d_pats, pats + b0, b1 - b0, cudaMemcpyHostToDevice, st));
-        SAB_CUDA_TRY(cudaMemcpyAsync(r.d_offs, offs + q0, (cnt + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+        // Chunks of SAB_SEARCH_CHUNK patterns alternate between two streams: the pattern upload of one chunk and
+        // the result download of another run under the kernel of a third (pinned caller buffers; PCIe is full
+        // duplex).  Every chunk owns its sub-ranges of the scratch buffers, so the streams never meet.
         const u8* adj = r.d_pats - b0;  // the kernel indexes patterns by their absolute offsets
-        if (mode == 0) SAB_TRY(launch_search<0>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
-        else if (mode == 1) SAB_TRY(launch_search<1>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
-        else SAB_TRY(launch_search<2>(r, ix->n, adj, r.d_offs, cnt, r.d_out0, r.d_out1));
-        if (mode == 1) {
-            SAB_CUDA_TRY(cudaMemcpyAsync((u8*)out0 + q0, r.d_out0, cnt, cudaMemcpyDeviceToHost, st));
-        } else {
-            SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out0 + q0, r.d_out0, cnt * sizeof(u32), cudaMemcpyDeviceToHost, st));
-            SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out1 + q0, r.d_out1, cnt * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        int which = 0;
+        for (u64 c0 = 0; c0 < cnt; c0 += SAB_SEARCH_CHUNK, which ^= 1) {
+            const u64 c1 = c0 + SAB_SEARCH_CHUNK < cnt ? c0 + SAB_SEARCH_CHUNK : cnt;
+            const u64 cc = c1 - c0;
+            const u64 cb0 = offs[q0 + c0], cb1 = offs[q0 + c1];
+            cudaStream_t st = (which && r.stream2) ? r.stream2 : r.ctx->stream;
+            if (cb1 > cb0) SAB_CUDA_TRY(cudaMemcpyAsync(r.d_pats + (cb0 - b0), pats + cb0, cb1 - cb0, cudaMemcpyHostToDevice, st));
+            // chunk c reads offs[c0 .. c1]; entry c1 is also the first of the next chunk, which lives one slot further
+            u64* d_offs = r.d_offs + c0 + c0 / SAB_SEARCH_CHUNK;
+            SAB_CUDA_TRY(cudaMemcpyAsync(d_offs, offs + q0 + c0, (cc + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+            u32* o0 = r.d_out0 + c0;
+            u32* o1 = r.d_out1 + c0;
+            if (mode == 0) SAB_TRY(launch_search<0>(r, ix->n, adj, d_offs, cc, o0, o1, ix->count_probes, st));
+            else if (mode == 1) SAB_TRY(launch_search<1>(r, ix->n, adj, d_offs, cc, (u32*)((u8*)r.d_out0 + c0), o1, false, st));
+            else SAB_TRY(launch_search<2>(r, ix->n, adj, d_offs, cc, o0, o1, false, st));
+            if (mode == 1) {
+                SAB_CUDA_TRY(cudaMemcpyAsync((u8*)out0 + q0 + c0, (u8*)r.d_out0 + c0, cc, cudaMemcpyDeviceToHost, st));
+            } else {
+                SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out0 + q0 + c0, o0, cc * sizeof(u32), cudaMemcpyDeviceToHost, st));
+                SAB_CUDA_TRY(cudaMemcpyAsync((u32*)out1 + q0 + c0, o1, cc * sizeof(u32), cudaMemcpyDeviceToHost, st));
+            }
         }
     }
     for (int d = 0; d < P; ++d) {
         SabReplica& r = ix->rep[d];
         SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
         SAB_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
+        if (r.stream2) SAB_CUDA_TRY(cudaStreamSynchronize(r.stream2));
     }
     return SAB_OK;
 }
@@ -750,9 +844,36 @@ extern "C" int32_t sab200_search_all_batch_device(sab200_index* ix, const uint8_
     std::lock_guard<std::mutex> lk(ix->mu);
     SabReplica& r = ix->rep[0];
     SAB_CUDA_TRY(cudaSetDevice(r.ctx->device));
-    SAB_TRY(launch_search<0>(r, ix->n, d_pats, d_offs, np, d_lo, d_hi));
+    SAB_TRY(launch_search<0>(r, ix->n, d_pats, d_offs, np, d_lo, d_hi, ix->count_probes));
     SAB_CUDA_TRY(cudaStreamSynchronize(r.ctx->stream));
     return SAB_OK;
+}
+
+// Probe counting for the roofline of the search kernel (bench.py): while on, search_all adds the suffix comparisons
+// of every pattern to a device counter (one atomic per pattern -- not for timed runs); returns the sum over the
+// replicas since the index was created.
+extern "C" uint64_t sab200_index_probes(sab200_index* ix, int32_t count_on) {
+    if (!ix) return 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->count_probes = count_on != 0;
+    u64 total = 0;
+    for (auto& r : ix->rep) {
+        if (!r.d_probes) continue;
+        unsigned long long v = 0;
+        cudaSetDevice(r.ctx->device);
+        cudaStreamSynchronize(r.ctx->stream);
+        if (cudaMemcpy(&v, r.d_probes, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) total += v;
+    }
+    return total;
+}
+
+// Layout of the prefix directory of replica 0: *sigma = base, *depth = symbols per code; returns the number of
+// entries (0: no directory).
+extern "C" uint64_t sab200_index_directory(sab200_index* ix, uint32_t* sigma, uint32_t* depth) {
+    if (!ix || ix->rep.empty() || !ix->rep[0].pd.dir) return 0;
+    if (sigma) *sigma = ix->rep[0].pd.sigma;
+    if (depth) *depth = ix->rep[0].pd.depth;
+    return ix->rep[0].pd.pw[ix->rep[0].pd.depth];
 }
 
 // ---- pack serialisation ---------------------------------------------------------------------

@@ -38,9 +38,13 @@
 #define SAB_GSORT_ITEMS 8
 #define SAB_GSORT_TILE (SAB_GSORT_THREADS * SAB_GSORT_ITEMS)
 #define SAB_GSORT_CAP (SAB_GSORT_TILE + SAB_GSORT_MID)  // tile + the tail of its last group
-#define SAB_GSORT_SMEM ((SAB_GSORT_CAP + 2) * 8 + SAB_GSORT_CAP * 8 + SAB_GSORT_CAP * 4 * 2 + (SAB_GSORT_TILE + 8) * 2)
+#define SAB_GSORT_MIDLIST 96  // more than SAB_GSORT_CAP / (SAB_GSORT_MAX + 1) groups of moderate size per tile
+// keys + payloads as they arrive, second ranks + payloads in output order (the first rank of a slot does not change:
+// a record only moves inside its group), head positions, list of the groups of moderate size: 54.7 KB, 4 CTAs / SM
+#define SAB_GSORT_SMEM ((SAB_GSORT_CAP + 2) * 8 + SAB_GSORT_CAP * 4 * 3 + (SAB_GSORT_TILE + 8) * 2 + SAB_GSORT_MIDLIST * 2)
 #define SAB_GSORT_NOGROUP 0xffffffffu  // never a rank (ranks are <= n <= 2^32 - 2)
 static_assert(SAB_GSORT_MID < SAB_GSORT_TILE && SAB_GSORT_MID >= SAB_GSORT_MAX, "a group the owner completes is shorter than a tile");
+static_assert(SAB_GSORT_CAP / (SAB_GSORT_MAX + 1) < SAB_GSORT_MIDLIST, "list of the groups of moderate size");
 static_assert(SAB_GSORT_THREADS == SAB_SCAN_THREADS, "warp_aggregates is sized for the scan kernels' block");
 
 struct CountOp {
@@ -48,12 +52,11 @@ struct CountOp {
 };
 
 // One warp orders `size` (<= 32 * IPL) records of one group, staged at s_in/s_vin, by (second rank, index) and
-// writes them to s_out/s_vout.  Element e of the group lives in register e / 32 of lane e % 32, so a
+// writes second ranks and indices to s_out/s_vout.  Element e of the group lives in register e / 32 of lane e % 32, so a
 // compare-exchange at distance >= 32 stays inside the lane and one at distance < 32 is a shuffle.
 template <int IPL>
-__device__ __forceinline__ void warp_sort_group(const u64* s_in, const u32* s_vin, u64* s_out, u32* s_vout, u32 size, u32 lane) {
+__device__ __forceinline__ void warp_sort_group(const u64* s_in, const u32* s_vin, u32* s_out, u32* s_vout, u32 size, u32 lane) {
     u64 x[IPL];
-    const u64 hi = s_in[0] & 0xffffffff00000000ull;
 #pragma unroll
     for (int j = 0; j < IPL; ++j) {
         const u32 e = (u32)j * 32u + lane;
@@ -91,7 +94,7 @@ __device__ __forceinline__ void warp_sort_group(const u64* s_in, const u32* s_vi
     for (int j = 0; j < IPL; ++j) {
         const u32 e = (u32)j * 32u + lane;
         if (e < size) {
-            s_out[e] = hi | (x[j] >> 32);
+            s_out[e] = (u32)(x[j] >> 32);
             s_vout[e] = (u32)x[j];
         }
     }
@@ -100,7 +103,7 @@ __device__ __forceinline__ void warp_sort_group(const u64* s_in, const u32* s_vi
 // Record p of the staged tile, member of group g (an index into s_heads; < 0: the group began in an earlier
 // tile): a record of a small group takes its output slot, a record of a big group keeps its place.  Returns
 // whether the record belongs to a big group.
-__device__ __forceinline__ bool gsort_place(const u64* s_key, const u32* s_val, u64* s_okey, u32* s_oval, const u16* s_heads, u32 p,
+__device__ __forceinline__ bool gsort_place(const u64* s_key, const u32* s_val, u32* s_or2, u32* s_oval, const u16* s_heads, u32 p,
                                             int g, u32 G, u32 tail_big, u32 lead_big) {
     const u64 key = s_key[p + 1];
     bool big = false;
@@ -116,12 +119,12 @@ __device__ __forceinline__ bool gsort_place(const u64* s_key, const u32* s_val, 
                 const u64 o = s_key[q + 1];
                 before += (o < key || (o == key && q < p)) ? 1u : 0u;
             }
-            s_okey[a + before] = key;
+            s_or2[a + before] = (u32)key;
             s_oval[a + before] = s_val[p];
         }
     }
     if (big) {
-        s_okey[p] = key;
+        s_or2[p] = (u32)key;
         s_oval[p] = s_val[p];
     }
     return big;
@@ -133,11 +136,13 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
                   u32 big_cap, u32* __restrict__ d_nbig, TileState<u32> st) {
     SAB_DYN_SMEM(smem);
     u64* s_key = (u64*)smem;                    // [0] the record before the tile, [1 + p] record p of the tile (+ tail)
-    u64* s_okey = s_key + SAB_GSORT_CAP + 2;    // the records in output order
-    u32* s_val = (u32*)(s_okey + SAB_GSORT_CAP);
-    u32* s_oval = s_val + SAB_GSORT_CAP;
+    u32* s_val = (u32*)(s_key + SAB_GSORT_CAP + 2);
+    u32* s_or2 = s_val + SAB_GSORT_CAP;         // second ranks and payloads in output order
+    u32* s_oval = s_or2 + SAB_GSORT_CAP;
     u16* s_heads = (u16*)(s_oval + SAB_GSORT_CAP);  // positions of the group heads inside the tile, then the end
+    u16* s_mid = s_heads + SAB_GSORT_TILE + 8;      // groups of moderate size (all but the tile's last group)
     SAB_SHARED_ARRAY(u32, s_edge, 4);           // tail length, tail group is big, leading records to skip, ... are big
+    SAB_SHARED_VAR(u32, s_nmid);
     const u32 tile = blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const u64 base = (u64)tile * SAB_GSORT_TILE;
     const u32 valid = (m - base < (u64)SAB_GSORT_TILE) ? (u32)(m - base) : (u32)SAB_GSORT_TILE;
@@ -150,7 +155,20 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
             s_val[p] = vin[base + p];
         }
     }
-    if (tid == 0) s_key[0] = base > 0 ? kin[base - 1] : none;
+    if (tid == 0) {
+        s_key[0] = base > 0 ? kin[base - 1] : none;
+        s_nmid = 0;
+    }
+    // the 32 records behind the tile (warp 0) and the 32 keys in front of it (warp 1) are requested together with
+    // the tile: step 2 below normally needs no more than these, so it adds no round trip of its own
+    u64 edge_key = none;
+    u32 edge_val = 0;
+    if (w == 0 && base + valid + lane < m) {
+        edge_key = kin[base + valid + lane];
+        edge_val = vin[base + valid + lane];
+    } else if (w == 1 && base >= (u64)lane + 1) {
+        edge_key = kin[base - 1 - lane];
+    }
     __syncthreads();
 
     // 1. group heads.  Warp w owns records [w*256, (w+1)*256) of the tile; item k of lane l is record w*256 + k*32 + l.
@@ -194,11 +212,11 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
                     const u64 g = base + valid + j;
                     bool eq = j < budget && g < m;
                     if (eq) {
-                        const u64 key = kin[g];
+                        const u64 key = off == 0 ? edge_key : kin[g];
                         eq = (u32)(key >> 32) == r1t;
                         if (eq && valid + j < SAB_GSORT_CAP) {
                             s_key[valid + 1 + j] = key;
-                            s_val[valid + j] = vin[g];
+                            s_val[valid + j] = off == 0 ? edge_val : vin[g];
                         }
                     }
                     const u32 bal = __ballot_sync(SAB_FULL, eq);
@@ -231,7 +249,7 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
                 for (u32 off = 0; off < budget; off += 32) {
                     const u32 j = off + lane;
                     bool eq = j < budget && base >= (u64)j + 1;
-                    if (eq) eq = (u32)(kin[base - 1 - j] >> 32) == r1f;
+                    if (eq) eq = (u32)((off == 0 ? edge_key : kin[base - 1 - j]) >> 32) == r1f;
                     const u32 bal = __ballot_sync(SAB_FULL, eq);
                     if (bal != SAB_FULL) {
                         const u32 jf = off + (u32)(__ffs((int)~bal) - 1);
@@ -248,6 +266,12 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
             s_edge[2] = skip;
             s_edge[3] = lead_big;
         }
+    } else {
+        // meanwhile the other warps list the groups of moderate size (the tile's last group is not complete yet)
+        for (u32 g = (w - 2) * 32 + lane; g + 1 < G; g += (SAB_SCAN_WARPS - 2) * 32) {
+            const u32 size = (u32)s_heads[g + 1] - (u32)s_heads[g];
+            if (size > SAB_GSORT_MAX && size <= SAB_GSORT_MID) s_mid[atomicAdd(&s_nmid, 1u)] = (u16)g;
+        }
     }
     __syncthreads();
     const u32 ext = s_edge[0], tail_big = s_edge[1], skip = s_edge[2], lead_big = s_edge[3];
@@ -259,24 +283,32 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
 #pragma unroll
     for (int k = 0; k < SAB_GSORT_ITEMS; ++k) {
         const u32 p = w * (32 * SAB_GSORT_ITEMS) + k * 32 + lane;
-        const bool big = p < valid && gsort_place(s_key, s_val, s_okey, s_oval, s_heads, p, gidx[k], G, tail_big, lead_big);
+        const bool big = p < valid && gsort_place(s_key, s_val, s_or2, s_oval, s_heads, p, gidx[k], G, tail_big, lead_big);
         bigb[k] = __ballot_sync(SAB_FULL, big);
         mine += (u32)__popc(bigb[k]);
     }
     // the fetched tail of the last group (a group that is small or of moderate size: never "big")
-    if (tid < ext) gsort_place(s_key, s_val, s_okey, s_oval, s_heads, valid + tid, (int)G - 1, G, tail_big, lead_big);
+    if (tid < ext) gsort_place(s_key, s_val, s_or2, s_oval, s_heads, valid + tid, (int)G - 1, G, tail_big, lead_big);
 
     // 4. groups of moderate size: one warp each, in registers
-    for (u32 g = w; g < G; g += SAB_SCAN_WARPS) {
+    const u32 nmid = s_nmid;
+    for (u32 t = w; t <= nmid; t += SAB_SCAN_WARPS) {
+        u32 g;
+        if (t < nmid) {
+            g = s_mid[t];
+        } else {  // the tile's last group, now that its tail is known
+            if (G == 0 || tail_big) break;
+            g = G - 1;
+        }
         const u32 a = s_heads[g], size = (u32)s_heads[g + 1] - a;
-        if (size <= SAB_GSORT_MAX || size > SAB_GSORT_MID || (g + 1 == G && tail_big)) continue;
-        if (size <= 64) warp_sort_group<2>(s_key + 1 + a, s_val + a, s_okey + a, s_oval + a, size, lane);
-        else if (size <= 128) warp_sort_group<4>(s_key + 1 + a, s_val + a, s_okey + a, s_oval + a, size, lane);
+        if (size <= SAB_GSORT_MAX || size > SAB_GSORT_MID) continue;
+        if (size <= 64) warp_sort_group<2>(s_key + 1 + a, s_val + a, s_or2 + a, s_oval + a, size, lane);
+        else if (size <= 128) warp_sort_group<4>(s_key + 1 + a, s_val + a, s_or2 + a, s_oval + a, size, lane);
 #if SAB_GSORT_MID > 128
-        else if (size <= 256) warp_sort_group<8>(s_key + 1 + a, s_val + a, s_okey + a, s_oval + a, size, lane);
+        else if (size <= 256) warp_sort_group<8>(s_key + 1 + a, s_val + a, s_or2 + a, s_oval + a, size, lane);
 #endif
 #if SAB_GSORT_MID > 256
-        else warp_sort_group<16>(s_key + 1 + a, s_val + a, s_okey + a, s_oval + a, size, lane);
+        else warp_sort_group<16>(s_key + 1 + a, s_val + a, s_or2 + a, s_oval + a, size, lane);
 #endif
     }
 
@@ -301,7 +333,7 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
     if (tid == 0 && base + SAB_GSORT_TILE >= m) *d_nbig = prefix + total;  // last tile
     __syncthreads();
     for (u32 p = skip + tid; p < cnt; p += SAB_GSORT_THREADS) {
-        kout[base + p] = s_okey[p];
+        kout[base + p] = (s_key[p + 1] & 0xffffffff00000000ull) | (u64)s_or2[p];  // a slot keeps its first rank
         vout[base + p] = s_oval[p];
     }
 }

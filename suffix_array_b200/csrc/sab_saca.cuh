@@ -27,9 +27,10 @@
 #include "sab_group_sort.cuh"
 
 // The bucket directory of the lazy inverse suffix array has 2^(ceil(log2 n) - SAB_DIR_SHIFT) entries (at most
-// 2^28): ~2^SAB_DIR_SHIFT sorted keys per entry for the gallop + bisect that follows the jump.
+// 2^28): ~2^SAB_DIR_SHIFT sorted keys per entry for the gallop + bisect that follows the jump.  Measured on the
+// 1 GiB DNA-like text (profiles/r02_ab_round2.txt): shift 4 -> 2 takes the gathers from 6.9 to 6.2 ms.
 #ifndef SAB_DIR_SHIFT
-#define SAB_DIR_SHIFT 4
+#define SAB_DIR_SHIFT 2
 #endif
 
 #define SAB_RANK_EMPTY 0xffffffffu

@@ -12,8 +12,11 @@
 #include "sab_context.cuh"
 
 #define SAB_BKT_LEN 65793u
+#ifndef SAB_SEARCH_G
 #define SAB_SEARCH_G 8
+#endif
 #define SAB_SEARCH_THREADS 256
+#define SAB_PDIR_MAXD 27  // deepest prefix directory: 2^27 entries over a binary alphabet
 
 // ------------------------------------------------------------------ enable_buckets
 // Dense path: the byte pairs are counted in a shared table indexed by (code(c0), code'(c1)) of the
@@ -102,7 +105,72 @@ __device__ __forceinline__ u32 load_be32(const u8* __restrict__ base, u64 off) {
     return __byte_perm(v, 0u, 0x0123u);
 }
 
+// Prefix directory of a resident index (built by sab200_index_create, invisible at the API): the suffixes are
+// coded by their first `depth` symbols as numbers in base sigma (symbol = number of smaller byte values present in
+// the text, the minimum symbol past the end of the text -- the code never decreases along the suffix array) and
+// dir[c] = number of suffixes with a code < c.  search_all / contains start their bisection from
+// [dir[c_lo], dir[c_hi]) of the pattern's code range instead of the whole two-byte bucket (1 GiB DNA-like text:
+// 2^26 entries, ~16 suffixes each, against buckets of 2^26 suffixes); the result is the same index pair, because
+// every suffix in front of the range is smaller than the pattern and every suffix behind it greater.
+struct PrefixDir {
+    const u32* dir;   // entries + 1 values, or null
+    const u16* lut;   // byte -> (number of present byte values below it) | 0x8000 if the byte occurs in the text
+    u32 sigma;        // base (>= 2)
+    u32 depth;        // symbols per code
+    u64 pw[SAB_PDIR_MAXD + 1];  // sigma^r
+};
+
+// code of the suffix at p (depth symbols, Horner)
+__device__ __forceinline__ u64 prefix_code(const u8* __restrict__ text, u64 n, u64 p, const u16* __restrict__ lut, u32 sigma, u32 depth) {
+    u64 c = 0;
+    for (u32 t = 0; t < depth; ++t) c = c * sigma + ((p + t < n) ? (u64)(lut[text[p + t]] & 0x1ffu) : 0ull);
+    return c;
+}
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(u32* __restrict__ out, u64 count, u32 value) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = value;
+}
+
+// dir[c] = j for every code c in (code(sa[j-1]), code(sa[j])]; the caller pre-fills dir with len (codes behind the
+// last suffix).  Short runs are written by their thread, long ones (codes no suffix has) by the whole warp.
+__global__ void __launch_bounds__(256)
+prefix_dir_kernel(const u8* __restrict__ text, u64 n, const u32* __restrict__ sa, u64 len, const u16* __restrict__ lut, u32 sigma,
+                  u32 depth, u32* __restrict__ dir) {
+    SAB_SHARED_ARRAY(u16, s_lut, 256);
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = lane_id();
+    u64 c = 0, first = 0, run = 0;
+    if (j < len) {
+        const u64 p = sa[j];
+        c = prefix_code(text, n, p <= n ? p : n, s_lut, sigma, depth);
+    }
+    u64 cp = __shfl_up_sync(SAB_FULL, c, 1);
+    if (lane == 0 && j > 0 && j < len) {
+        const u64 p = sa[j - 1];
+        cp = prefix_code(text, n, p <= n ? p : n, s_lut, sigma, depth);
+    }
+    if (j < len) {
+        first = j == 0 ? 0 : cp + 1;       // a corrupt array (codes not ascending) writes nothing out of order
+        run = c + 1 > first ? c + 1 - first : 0;
+    }
+    if (run <= 8)
+        for (u64 t = 0; t < run; ++t) dir[first + t] = (u32)j;
+    u32 todo = __ballot_sync(SAB_FULL, run > 8);
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const u64 f = __shfl_sync(SAB_FULL, first, src), r = __shfl_sync(SAB_FULL, run, src);
+        const u32 v = (u32)(j - lane + (u64)src);
+        for (u64 t = lane; t < r; t += 32) dir[f + t] = v;
+    }
+}
+
 struct SearchArgs {
+    PrefixDir pd;
+    unsigned long long* probes;  // cumulative number of probes (suffix comparisons), or null
     const u8* text;   // n bytes (+ padding)
     u64 n;
     const u32* sa;    // n + 1
@@ -193,9 +261,38 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
         }
         return;
     }
+    if (MODE != 2 && a.pd.dir) {
+        // narrow [lo, hi) to the suffixes that share the pattern's first symbols (search_lcp keeps the reference's
+        // range: its answer depends on the borders of the two-byte bucket, src/sa.rs:224-252)
+        const u32 depth = a.pd.depth, sigma = a.pd.sigma;
+        u64 code = 0;
+        u32 t = 0, e = 0x8000u;
+        for (; t < depth && t < m; ++t) {
+            e = a.pd.lut[pat[t]];
+            if (!(e & 0x8000u)) break;
+            code = code * sigma + (e & 0x1ffu);
+        }
+        u64 clo, chi;
+        if (e & 0x8000u) {  // t symbols of the pattern, all present in the text: every code that starts with them
+            clo = code * a.pd.pw[depth - t];
+            chi = clo + a.pd.pw[depth - t];
+        } else {
+            // byte t of the pattern does not occur in the text: the pattern falls between two neighbouring codes --
+            // unless it is smaller than every symbol, where it still follows the suffixes that END after the t
+            // symbols (they are padded with the minimum symbol and share the first code of the prefix)
+            clo = (code * sigma + (e & 0x1ffu)) * a.pd.pw[depth - t - 1];
+            chi = clo + ((e & 0x1ffu) == 0 ? 1u : 0u);
+        }
+        const u64 dlo = a.pd.dir[clo], dhi = a.pd.dir[chi];
+        if (dlo > lo) lo = dlo;
+        if (dhi < hi) hi = dhi;
+        if (hi < lo) hi = lo;
+    }
+    u32 nprobe = 0;
     // lower bound: first index whose suffix is not < pat   (src/sa.rs:181-190)
     u64 i = lo, k = hi;
     while (i < k) {
+        ++nprobe;
         const u64 mid = i + (k - i) / 2;
         const u64 p = a.sa[mid];
         u32 less_at;
@@ -216,6 +313,7 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
         for (u64 step = 1; j < k; step <<= 1) {
             const u64 t = (k - j > step) ? j + step - 1 : k - 1;
             u32 less_at;
+            ++nprobe;
             const u64 d = group_compare<G>(a, pat, m, a.sa[t], gmask, gl, gbase, pw0, pw1, &less_at);
             if (d == m) {
                 j = t + 1;
@@ -228,6 +326,7 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
             const u64 mid = j + (k - j) / 2;
             const u64 p = a.sa[mid];
             u32 less_at;
+            ++nprobe;
             const u64 d = group_compare<G>(a, pat, m, p, gmask, gl, gbase, pw0, pw1, &less_at);
             if (d == m) j = mid + 1;
             else k = mid;
@@ -235,6 +334,7 @@ __global__ void __launch_bounds__(SAB_SEARCH_THREADS) search_kernel(SearchArgs a
         if (gl == 0) {
             a.out0[q] = (u32)i;
             a.out1[q] = (u32)j;
+            if (a.probes) atomicAdd(a.probes, (unsigned long long)nprobe);
         }
     } else if (MODE == 1) {
         // src/sa.rs:168-169: a suffix whose truncation equals pat exists iff the lower bound starts with pat

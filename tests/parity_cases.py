@@ -301,3 +301,36 @@ def group_sort_cases(rng):
     for c in list(cases[-9:-3]) + [cases[20], cases[30]]:
         cases.append((c[0], c[1], False))
     return cases
+
+
+def directory_query_cases(rng):
+    """(text, patterns) aimed at the prefix directory of the resident index (csrc/sab_search.cuh PrefixDir): alphabets
+    with gaps, patterns shorter / longer than the directory depth, patterns that end the text, bytes that do not
+    occur in the text below / between / above the symbols at every position, the empty pattern."""
+    out = []
+    for alphabet, n in (([5, 9, 200], 5000), ([0, 1], 3000), ([255], 400), ([0], 300), ([0, 255], 2500),
+                        ([7, 8, 9, 10, 250], 70000), (list(range(256)), 20000), ([65, 67, 71, 84], 200000)):
+        alphabet = np.array(alphabet, dtype=np.uint8)
+        s = alphabet[rng.integers(0, alphabet.size, n)]
+        if n > 1000:
+            s[n // 2:n // 2 + 300] = s[:300]  # a repeat, so that ranges are longer than one suffix
+        pats = [b"", s.tobytes()[-1:], s.tobytes()[-5:], s.tobytes()[-40:], s.tobytes()[:70]]
+        absent = [b for b in (0, 1, 4, 6, 8, 66, 100, 199, 201, 254, 255) if b not in alphabet.tolist()]
+        for _ in range(150):
+            m = int(rng.integers(1, 48))
+            i = int(rng.integers(0, n - m + 1))
+            p = bytearray(s[i:i + m].tobytes())
+            kind = int(rng.integers(0, 4))
+            if kind == 1 and absent:
+                p[int(rng.integers(0, m))] = int(rng.choice(absent))
+            elif kind == 2:
+                p[int(rng.integers(0, m))] = int(rng.choice(alphabet))
+            elif kind == 3 and absent:
+                p = p[:int(rng.integers(0, m))] + bytes([int(rng.choice(absent))])
+            pats.append(bytes(p))
+        for b in absent[:6]:
+            pats.append(bytes([b]))
+            pats.append(bytes([b, int(alphabet[0])]))
+            pats.append(bytes([int(alphabet[-1]), b]))
+        out.append((s, pats))
+    return out

@@ -51,6 +51,18 @@ def test_emu_queries(emu_backend, oracle):
     pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
 
 
+def test_emu_prefix_directory_queries(emu_backend, oracle):
+    """The prefix directory must not change a single answer: search_all / contains / search_lcp against the oracle
+    on alphabets with gaps and patterns with bytes the text does not contain (see pc.directory_query_cases)."""
+    import ctypes as C
+    rng = np.random.default_rng(404)
+    for s, pats in pc.directory_query_cases(rng):
+        sa = pc.check_queries(oracle, s, pats)
+        sigma, depth = C.c_uint32(), C.c_uint32()
+        entries = emu_backend.sab200_index_directory(sa._get_index(), C.byref(sigma), C.byref(depth))
+        assert entries == int(sigma.value) ** int(depth.value) and entries >= 2, (entries, sigma.value, depth.value)
+
+
 def test_emu_fused_buckets(emu_backend, oracle):
     """Bucket table from the sorted keys of the construction: absent bytes, \\0 / \\xff, one symbol per key (falls
     back to the pair counting over the resident text), all 256 byte values, 255 values (radix 2^8: base^k = 2^64)."""

@@ -103,6 +103,18 @@ def test_queries_vs_oracle(gpu_lib, oracle):
     pc.check_queries(oracle, np.frombuffer(b"", dtype=np.uint8), [b"", b"a", b"ab"])
 
 
+def test_prefix_directory_queries(gpu_lib, oracle):
+    # the prefix directory of the resident index must not change a single answer (alphabets with gaps, bytes the
+    # text does not contain at every position, patterns shorter / longer than the directory depth)
+    import ctypes as C
+    rng = np.random.default_rng(404)
+    for s, pats in pc.directory_query_cases(rng):
+        sa = pc.check_queries(oracle, s, pats)
+        sigma, depth = C.c_uint32(), C.c_uint32()
+        entries = gpu_lib.sab200_index_directory(sa._get_index(), C.byref(sigma), C.byref(depth))
+        assert entries == int(sigma.value) ** int(depth.value) and entries >= 2
+
+
 def test_queries_sharded_over_replicas(gpu_lib, oracle):
     # the index is replicated, the patterns are sharded over the GPUs, no collective
     ngpus = min(4, gpu_lib.sab200_device_count())
