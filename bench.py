@@ -293,7 +293,7 @@ def bench_search(L, _lib, torch, dev, text, sa, n, ngpus, npat, sample=1_000_000
             sector = int(probes * per_probe_sector + 3 * 32 * npat)
             rec.update({"queries_per_s_kernel": round(npat / best, 1), "kernel_ms": round(best * 1e3, 3),
                         "device_equals_host": bool(np.array_equal(d_lo.cpu().numpy().view(np.uint32), lo)),
-                        "roofline": {"bound": "hbm (dependent random 32-byte sectors)", "kernel": "search_kernel<8, search_all>",
+                        "roofline": {"bound": "hbm (dependent random 32-byte sectors)", "kernel": "search_kernel<4, search_all> (4 lanes per pattern)",
                                      "probes": probes, "probes_per_query": round(probes / npat, 2),
                                      "algorithmic_bytes": algo, "sector_bytes": sector,
                                      "achieved": round(algo / 1e9 / best, 1), "achieved_sector": round(sector / 1e9 / best, 1),

@@ -29,6 +29,9 @@
 // The bucket directory of the lazy inverse suffix array has 2^(ceil(log2 n) - SAB_DIR_SHIFT) entries (at most
 // 2^28): ~2^SAB_DIR_SHIFT sorted keys per entry for the gallop + bisect that follows the jump.  Measured on the
 // 1 GiB DNA-like text (profiles/r02_ab_round2.txt): shift 4 -> 2 takes the gathers from 6.9 to 6.2 ms.
+#ifndef SAB_GS_REQUIRE_SORTED
+#define SAB_GS_REQUIRE_SORTED 0  // debugging aid: 1 = the in-group sort only runs on lists ascending in r1
+#endif
 #ifndef SAB_DIR_SHIFT
 #define SAB_DIR_SHIFT 2
 #endif
@@ -608,6 +611,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             if (n_sort * 10 > m * 7) filter_on = false;  // from here on most groups split every round
         }
         u64 kept = 0;
+        bool order_restored = false;  // the round's records went through the full radix sort: ascending in r1 again
         if (n_sort > 0) {
             // sort the n_sort records at the front of (k[cur], v[cur]); the spare payload buffer starts
             // behind the n_stay records already parked in v[cur^1]
@@ -620,7 +624,7 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             // 5d. small groups are ordered in one sweep; the spare buffers for the records of big groups are
             // the unused tails of the round buffers (keys, payloads) and of r1buf (positions)
             int sorted = 0;
-            if (group_sort_on) {
+            if (group_sort_on && (list_sorted || !SAB_GS_REQUIRE_SORTED)) {
                 const u64 used = sab_align_up(n_sort, 64);
                 const u64 cap_keys = key_cap > used ? key_cap - used : 0;
                 const u64 cap_vals = n + 8 > n_stay + used ? n + 8 - n_stay - used : 0;
@@ -644,7 +648,10 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
                     --gs_pause;
                 }
             }
-            if (!sorted) SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+            if (!sorted) {
+                SAB_TRY(sab_radix_sort<u64>(c, sb, n_sort, 0, 32 + rank_bits, /*iota=*/false, &S.passes[round]));
+                order_restored = true;
+            }
             u32* out_idx = (sb.cur == 0) ? rb.v[rb.cur ^ 1] + n_stay : rb.v[rb.cur];
             {
                 const u64 tiles = div_up64(n_sort, SAB_SCAN_TILE);
@@ -663,8 +670,9 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
             if (sb.cur != 0 && kept > 0)  // the survivors were written to the other buffer: append them to the parked ones
                 SAB_CUDA_TRY(cudaMemcpyAsync(rb.v[rb.cur ^ 1] + n_stay, rb.v[rb.cur], kept * sizeof(u32), cudaMemcpyDeviceToDevice, st));
         }
-        // parked records first, then the survivors of the sort (ascending either way it was sorted)
-        list_sorted = n_stay == 0;
+        // Parked records first, then the survivors of the sort.  The in-group sort keeps the records where they
+        // are: a list of several ascending runs stays one until a round takes the full radix sort.
+        list_sorted = n_stay == 0 && (list_sorted || order_restored);
         rb.cur ^= 1;
         m = n_stay + kept;
         S.active[round] = m;

@@ -12,8 +12,11 @@
 #include "sab_context.cuh"
 
 #define SAB_BKT_LEN 65793u
+// 4 lanes per pattern (16 bytes per compare step): with the prefix directory a query is ~7 probes and most of them
+// differ inside the first 16 bytes; 10 M patterns of 8..64 B on the 1 GiB index: 1.61 / 1.89 G queries/s against
+// 1.25 / 1.47 with 8 lanes (profiles/r02_search_variants.txt)
 #ifndef SAB_SEARCH_G
-#define SAB_SEARCH_G 8
+#define SAB_SEARCH_G 4
 #endif
 #define SAB_SEARCH_THREADS 256
 #define SAB_PDIR_MAXD 27  // deepest prefix directory: 2^27 entries over a binary alphabet

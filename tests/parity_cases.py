@@ -334,3 +334,24 @@ def directory_query_cases(rng):
             pats.append(bytes([int(alphabet[-1]), b]))
         out.append((s, pats))
     return out
+
+
+def parked_then_unsorted_text(rng, copies=600, zlen=64, ulen=40, lq=60000, la=1200, lr=100000):
+    """A text whose doubling rounds go: split filter parks large groups (600 copies of a block whose copies only
+    differ late) -> the next round sorts the two-run list with the in-group sweep -> a later round still holds
+    large groups in BOTH runs (the parked copies, high first ranks, in front of a run of 1200 equal bytes, low first
+    rank).  Regression for the round-2 bug where the list was taken for ascending again after a sweep round and the
+    radix-sorted records of large groups went back to the positions of other groups.  ~224 kB: seconds under the
+    emulator (production cost-model constant), milliseconds on the GPU."""
+    A, B, Cc, D = 97, 98, 99, 100
+    Z = rng.choice([Cc, D], zlen).astype(np.uint8)
+    P = np.concatenate([np.concatenate([Z, rng.choice([Cc, D], ulen).astype(np.uint8)]) for _ in range(copies)])
+    runs = []
+    for _ in range(lq // 300):  # periodic runs: groups of ~50 that lose a few members every round (never parked)
+        pat = rng.choice([A, B], int(rng.integers(5, 9))).astype(np.uint8)
+        runs.append(np.tile(pat, 300 // pat.size + 1)[:300])
+        runs.append(rng.choice([Cc, D], 3).astype(np.uint8))
+    Q = np.concatenate(runs)
+    S = np.full(la, A, dtype=np.uint8)
+    R = rng.choice([A, B, Cc, D], lr).astype(np.uint8)  # settled by the initial sort: spare room for the sweep
+    return np.concatenate([R, np.array([D], dtype=np.uint8), S, np.array([B], dtype=np.uint8), Q, P])

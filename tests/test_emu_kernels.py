@@ -198,6 +198,11 @@ def test_emu_randomized_construction(build, emu_lib, oracle, monkeypatch):
     rng = np.random.default_rng(2026)
     for _ in range(9):
         pc.check_construction(oracle, pc.random_text(rng))
+    if build == "emu-prod":
+        # split filter -> in-group sweep on a two-run list -> large groups in both runs (see the docstring)
+        pc.check_construction(oracle, pc.parked_then_unsorted_text(np.random.default_rng(1)))
+        st = _lib.last_stats()
+        assert st["group_big_records"] > 0 and st["group_sort_records"] > 2 * st["group_big_records"], st
 
 
 def test_emu_staged_pageable_copies(emu_lib):

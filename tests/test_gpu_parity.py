@@ -179,6 +179,9 @@ def test_filter_and_group_sort_rounds(gpu_lib, oracle):
         sa = SuffixArray(s)
         assert oracle.sufcheck(s, sa.sa), (block, mut, last_stats())
         assert SuffixArray.from_parts(s, sa.sa) is not None
+    # parked large groups, then the in-group sweep on the two-run list, then large groups in both runs
+    for seed in (1, 2, 3):
+        pc.check_construction(oracle, pc.parked_then_unsorted_text(np.random.default_rng(seed)))
 
 
 def test_group_sort_direct(gpu_lib):
