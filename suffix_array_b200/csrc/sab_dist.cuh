@@ -523,11 +523,8 @@ static int sab_dist_saca(sab200_comm* cm, SabContext* c, DistArena A0, const u8*
     SAB_ARENA_CHECK(A);
     if (count) {
         sab_prof_begin(c, 2);
-        SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, avail, count,
-                   (const u16*)d_lut, base, k, sab_pack_pow(base, k), keysA);
+        SAB_TRY(sab_launch_pack(c, d_text, avail, count, (const u16*)d_lut, base, k, keysA));
         sab_prof_end(c);
-        SAB_LAUNCH_CHECK();
-        S.kernel_launches++;
     }
     u64 splitters[SAB_MAX_RANKS];
     for (int i = 0; i < SAB_MAX_RANKS; ++i) splitters[i] = ~0ull;

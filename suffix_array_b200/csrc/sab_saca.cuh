@@ -165,6 +165,81 @@ pack_keys_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __res
     }
 }
 
+// Fast path of the key packing (round 2): when radix^ka < 2^32 for ka = ceil(k / 2), a key is two HALF keys of ka
+// symbols glued together,
+//     key(i) = (g(i) - sub) * W + g(i + s),   g(x) = sum_{t < ka} code(x + t) * radix^(ka - 1 - t)   (32 bits),
+//     k even: s = ka, W = radix^ka, sub = 0;   k odd: s = ka - 1, W = radix^(ka - 1), sub = code(i + ka - 1)
+// (for odd k the two windows overlap in one symbol, which is taken out of the first).  The half keys slide in
+// 32-bit arithmetic (two multiply-adds per position instead of two 64-bit multiply chains) and are staged in
+// shared memory; the final multiply-add is one 32 x 32 -> 64 bit instruction and the 8-byte stores are coalesced
+// without a second staging pass.  Same keys as pack_keys_kernel, bit for bit.
+__global__ void __launch_bounds__(SAB_PACK_THREADS)
+pack_keys_split_kernel(const u8* __restrict__ text, u64 n, u64 count, const u16* __restrict__ lut, u32 radix, int k, u32 wtop, u32 wmul,
+                       u64* __restrict__ keys) {
+    SAB_SHARED_ARRAY(u32, s_code, SAB_PACK_TILE + 64 + (SAB_PACK_TILE + 64) / 32 + 8);
+    SAB_SHARED_ARRAY(u16, s_lut, 256);
+    SAB_SHARED_ARRAY(u32, s_g, SAB_PACK_TILE + 32 + (SAB_PACK_TILE + 32) / 32 + 8);
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const u64 tile0 = (u64)blockIdx.x * SAB_PACK_TILE;
+    for (int o = threadIdx.x; o < SAB_PACK_TILE + 64; o += SAB_PACK_THREADS) {
+        const u64 i = tile0 + o;
+        s_code[SAB_PAD(o)] = i < n ? (u32)s_lut[text[i]] : 0u;
+    }
+    __syncthreads();
+    const int ka = (k + 1) / 2;
+    const int shift = (k & 1) ? ka - 1 : ka;
+    // half keys of the thread's SAB_PACK_ITEMS consecutive positions: Horner for the first, then the window slides;
+    // wtop = radix^(ka-1) is the weight of the symbol that leaves
+    {
+        const int o0 = threadIdx.x * SAB_PACK_ITEMS;
+        u32 g = 0;
+        for (int t = 0; t < ka; ++t) g = g * radix + s_code[SAB_PAD(o0 + t)];
+#pragma unroll
+        for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
+            s_g[SAB_PAD(o0 + j)] = g;
+            g = (g - s_code[SAB_PAD(o0 + j)] * wtop) * radix + s_code[SAB_PAD(o0 + j + ka)];
+        }
+    }
+    if (threadIdx.x < 32) {  // the 32 positions behind the tile that the second halves reach into
+        const int o = SAB_PACK_TILE + threadIdx.x;
+        u32 g = 0;
+        for (int t = 0; t < ka; ++t) g = g * radix + s_code[SAB_PAD(o + t)];
+        s_g[SAB_PAD(o)] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SAB_PACK_ITEMS; ++j) {
+        const int o = threadIdx.x + j * SAB_PACK_THREADS;
+        const u64 i = tile0 + o;
+        if (i < count) {
+            const u32 sub = (k & 1) ? s_code[SAB_PAD(o + shift)] : 0u;
+            keys[i] = (u64)(s_g[SAB_PAD(o)] - sub) * wmul + (u64)s_g[SAB_PAD(o + shift)];
+        }
+    }
+}
+
+// keys of positions [0, count) of a text (or shard + halo) of n readable bytes: picks the kernel
+static int sab_launch_pack(SabContext* c, const u8* d_text, u64 n, u64 count, const u16* d_lut, u32 base, int k, u64* keys) {
+    if (count == 0) return SAB_OK;
+    const int ka = (k + 1) / 2;
+    unsigned __int128 lim = 1;
+    for (int t = 0; t < ka; ++t) lim *= base;
+    const char* off = getenv("SAB_PACK_SPLIT");
+    if (k >= 2 && ka <= 32 && lim < ((unsigned __int128)1 << 32) && !(off && off[0] == '0')) {
+        const u32 wtop = (u32)sab_pow_u64(base, ka - 1);
+        const u32 wmul = (u32)sab_pow_u64(base, (k & 1) ? ka - 1 : ka);
+        SAB_LAUNCH(pack_keys_split_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, c->stream, d_text, n, count,
+                   d_lut, base, k, wtop, wmul, keys);
+    } else {
+        SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(count, SAB_PACK_TILE), SAB_PACK_THREADS, 0, c->stream, d_text, n, count, d_lut,
+                   base, k, sab_pack_pow(base, k), keys);
+    }
+    SAB_LAUNCH_CHECK();
+    c->stats.kernel_launches++;
+    return SAB_OK;
+}
+
 // ------------------------------------------------------------------ 4b. lazy inverse suffix array
 // Scattering all n initial ranks costs a partial-sector write per suffix (~30 G/s on B200, 35-50 ms per
 // GiB) although only i + h of the few active i are ever looked up.  So rank[] starts EMPTY except for
@@ -482,11 +557,8 @@ static int sab_saca_device(SabContext* c, const u8* d_text, u64 n, u32* d_sa) {
     SAB_CUDA_TRY(cudaMemcpyAsync(d_lut, c->h_small + 384, sizeof(lut), cudaMemcpyHostToDevice, st));
 
     // 2. packed keys
-    SAB_LAUNCH(pack_keys_kernel, (unsigned)div_up64(n, SAB_PACK_TILE), SAB_PACK_THREADS, 0, st, d_text, n, n,
-               (const u16*)d_lut, base, k, sab_pack_pow(base, k), buf.k[0]);
+    SAB_TRY(sab_launch_pack(c, d_text, n, n, (const u16*)d_lut, base, k, buf.k[0]));
     sab_prof_end(c);
-    SAB_LAUNCH_CHECK();
-    S.kernel_launches++;
 
     // 3. sort (key, i); the payload of the first pass is generated, not read
     // (the last pass writes the sorted indices straight into sa[1..]: they need no copy afterwards)
