@@ -92,60 +92,65 @@ __device__ __forceinline__ T warp_reduce_pod(T v, Op op) {
     return v;
 }
 
+// Look-back of one tile by ONE full warp: publishes `aggregate` (valid in lane 0) as the tile's PARTIAL, combines the
+// aggregates of all tiles < `tile` (op commutative + associative), publishes the INCLUSIVE value and returns the
+// exclusive prefix in every lane of the warp.  No block barrier inside: the other warps of the block may work on.
+// Tiles must be numbered in launch order (a tile may only wait on tiles whose blocks have already started):
+// blockIdx.x of a 1-D grid.
+template <typename T, typename Op>
+__device__ __forceinline__ T tile_exclusive_prefix_warp(const TileState<T>& st, u32 tile, T aggregate, Op op, T identity) {
+    const u32 lane = lane_id();
+    union {
+        T t;
+        u32 w[sizeof(T) / 4];
+    } bc;
+    bc.t = aggregate;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) bc.w[i] = __shfl_sync(SAB_FULL, bc.w[i], 0);
+    aggregate = bc.t;
+    const u32 tag = st.epoch << 2;
+    if (tile == 0) {
+        if (lane == 0) st_slot(&st.slots[0], make_slot<T>(tag | SCAN_INCLUSIVE, aggregate));
+        return identity;
+    }
+    if (lane == 0) st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_PARTIAL, aggregate));
+    T running = identity;
+    i64 base = (i64)tile - 1;
+    while (true) {
+        const i64 t = base - (i64)lane;
+        u32 f = SCAN_INCLUSIVE;  // virtual tiles before tile 0: inclusive identity
+        T val = identity;
+        if (t >= 0) {
+            while (true) {
+                const ScanSlot s = ld_slot(&st.slots[t]);
+                f = ((s.tag >> 2) == st.epoch) ? (s.tag & 3u) : (u32)SCAN_EMPTY;
+                if (f != SCAN_EMPTY) {
+                    val = slot_value<T>(s);
+                    break;
+                }
+                SAB_SPIN_PAUSE();
+            }
+        }
+        const u32 incl = __ballot_sync(SAB_FULL, f == SCAN_INCLUSIVE);
+        const u32 first = incl ? (u32)(__ffs((int)incl) - 1) : 31u;
+        if (lane > first) val = identity;
+        running = op(running, warp_reduce_pod(val, op));
+        if (incl) break;
+        base -= 32;
+    }
+    if (lane == 0) st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_INCLUSIVE, op(running, aggregate)));
+    return running;
+}
+
 // Returns, in every thread of the block, the combination (op, commutative + associative) of the
 // aggregates of all tiles < `tile`.  `aggregate` must be valid in thread 0.  Must be called by all
-// threads of the block (it contains __syncthreads).  Tiles must be numbered in launch order (a
-// tile may only wait on tiles whose blocks have already started): blockIdx.x of a 1-D grid.
+// threads of the block (it contains __syncthreads).  Tile numbering as above.
 template <typename T, typename Op>
 __device__ __forceinline__ T tile_exclusive_prefix(const TileState<T>& st, u32 tile, T aggregate, Op op, T identity) {
     SAB_SHARED_VAR(T, s_prefix);
     if (warp_id() == 0) {
-        const u32 lane = lane_id();
-        union {
-            T t;
-            u32 w[sizeof(T) / 4];
-        } bc;
-        bc.t = aggregate;
-#pragma unroll
-        for (int i = 0; i < (int)(sizeof(T) / 4); ++i) bc.w[i] = __shfl_sync(SAB_FULL, bc.w[i], 0);
-        aggregate = bc.t;
-        const u32 tag = st.epoch << 2;
-        if (tile == 0) {
-            if (lane == 0) {
-                st_slot(&st.slots[0], make_slot<T>(tag | SCAN_INCLUSIVE, aggregate));
-                s_prefix = identity;
-            }
-        } else {
-            if (lane == 0) st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_PARTIAL, aggregate));
-            T running = identity;
-            i64 base = (i64)tile - 1;
-            while (true) {
-                const i64 t = base - (i64)lane;
-                u32 f = SCAN_INCLUSIVE;  // virtual tiles before tile 0: inclusive identity
-                T val = identity;
-                if (t >= 0) {
-                    while (true) {
-                        const ScanSlot s = ld_slot(&st.slots[t]);
-                        f = ((s.tag >> 2) == st.epoch) ? (s.tag & 3u) : (u32)SCAN_EMPTY;
-                        if (f != SCAN_EMPTY) {
-                            val = slot_value<T>(s);
-                            break;
-                        }
-                        SAB_SPIN_PAUSE();
-                    }
-                }
-                const u32 incl = __ballot_sync(SAB_FULL, f == SCAN_INCLUSIVE);
-                const u32 first = incl ? (u32)(__ffs((int)incl) - 1) : 31u;
-                if (lane > first) val = identity;
-                running = op(running, warp_reduce_pod(val, op));
-                if (incl) break;
-                base -= 32;
-            }
-            if (lane == 0) {
-                st_slot(&st.slots[tile], make_slot<T>(tag | SCAN_INCLUSIVE, op(running, aggregate)));
-                s_prefix = running;
-            }
-        }
+        const T r = tile_exclusive_prefix_warp<T, Op>(st, tile, aggregate, op, identity);
+        if (lane_id() == 0) s_prefix = r;
     }
     __syncthreads();
     T r = s_prefix;

@@ -277,11 +277,20 @@ rerank_kernel(const u64* __restrict__ S, const u32* __restrict__ I, u64 m, u32* 
 __global__ void __launch_bounds__(256)
 mark_split_groups_kernel(const u64* __restrict__ key64, u64 m, u32* __restrict__ bitmap) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0 || j >= m) return;
-    const u64 a = key64[j - 1], b = key64[j];
-    if ((a >> 32) == (b >> 32) && (u32)a != (u32)b) {
-        const u32 r1 = (u32)(b >> 32);
-        atomicOr(&bitmap[r1 >> 5], 1u << (r1 & 31u));
+    bool split = false;
+    u32 r1 = 0;
+    if (j > 0 && j < m) {
+        const u64 a = key64[j - 1], b = key64[j];
+        r1 = (u32)(b >> 32);
+        split = (a >> 32) == (b >> 32) && (u32)a != (u32)b;
+    }
+    // One atomic per warp and group, and none once the bit is set: in a group of a million records nearly every
+    // neighbouring pair differs, and a million atomics on one word serialise in the L2 (natural-language texts:
+    // this kernel took longer than the sort of the round).
+    const u32 peers = __match_any_sync(SAB_FULL, split ? (u64)r1 : (0x100000000ull | lane_id()));
+    if (split && lane_id() == (u32)(__ffs((int)peers) - 1)) {
+        const u32 bit = 1u << (r1 & 31u);
+        if (!(ld_acquire_u32(&bitmap[r1 >> 5]) & bit)) atomicOr(&bitmap[r1 >> 5], bit);
     }
 }
 
