@@ -64,6 +64,15 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #endif
 }
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32* p) {
+#ifdef SAB_EMU
+    return *(const volatile u32*)p;
+#else
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
 #ifdef SAB_EMU
     return *(const volatile u64*)p;

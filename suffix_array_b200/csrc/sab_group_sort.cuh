@@ -22,6 +22,10 @@
 //                       list that is not ascending in r1 the positions are first sorted by the r1 of their
 //                       record, see sab_group_sort).
 //
+// Measured and rejected (profiles/r02_ab_round2_group_sort.txt): publishing the big-record counts before the sorting
+// so that the look-back runs beside the sorting warps -- 256 MiB repetitive text 45.4 -> 49.6 ms, 1 GiB DNA-like
+// text 1.8 -> 2.0 ms (the spinning look-back warp costs more issue slots than the barrier it removes).
+//
 // No reference counterpart: it replaces part of the work of divsufsort's group refinement
 // (third-party crate behind /root/reference/src/saca.rs:14).
 #pragma once
@@ -33,6 +37,9 @@
 #endif
 #ifndef SAB_GSORT_MID
 #define SAB_GSORT_MID 512  // largest group ordered by one warp in registers (64, 128, 256 or 512)
+#endif
+#ifndef SAB_GSORT_DYNAMIC
+#define SAB_GSORT_DYNAMIC 0  // 1: the warps of a tile take the moderate groups from a shared counter (A/B: no gain)
 #endif
 #define SAB_GSORT_THREADS 256
 #define SAB_GSORT_ITEMS 8
@@ -141,10 +148,11 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
     u32* s_oval = s_or2 + SAB_GSORT_CAP;
     u16* s_heads = (u16*)(s_oval + SAB_GSORT_CAP);  // positions of the group heads inside the tile, then the end
     u16* s_mid = s_heads + SAB_GSORT_TILE + 8;      // groups of moderate size (all but the tile's last group)
-    SAB_SHARED_ARRAY(u32, s_edge, 5);           // tail length, tail group is big, leading records to skip, ... are big,
-                                                // big records in the tiles before this one
+    SAB_SHARED_ARRAY(u32, s_edge, 4);           // tail length, tail group is big, leading records to skip, ... are big
     SAB_SHARED_VAR(u32, s_nmid);
+#if SAB_GSORT_DYNAMIC
     SAB_SHARED_VAR(u32, s_next);
+#endif
     const u32 tile = blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const u64 base = (u64)tile * SAB_GSORT_TILE;
     const u32 valid = (m - base < (u64)SAB_GSORT_TILE) ? (u32)(m - base) : (u32)SAB_GSORT_TILE;
@@ -160,7 +168,9 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
     if (tid == 0) {
         s_key[0] = base > 0 ? kin[base - 1] : none;
         s_nmid = 0;
+#if SAB_GSORT_DYNAMIC
         s_next = 0;
+#endif
     }
     // the 32 records behind the tile (warp 0) and the 32 keys in front of it (warp 1) are requested together with
     // the tile: step 2 below normally needs no more than these, so it adds no round trip of its own
@@ -280,47 +290,30 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
     const u32 ext = s_edge[0], tail_big = s_edge[1], skip = s_edge[2], lead_big = s_edge[3];
     const u32 cnt = valid + ext;
 
-    // 3. which records belong to big groups: their number is this tile's share of the compaction, published right
-    // away so that the look-back of the following tiles -- and this tile's own, run by warp 0 while the other warps
-    // already sort -- is over long before anybody needs the result
+    // 3. small groups by the counting rank; records of big groups keep their place (the scatter-back overwrites it)
     u32 bigb[SAB_GSORT_ITEMS];
     mine = 0;
 #pragma unroll
     for (int k = 0; k < SAB_GSORT_ITEMS; ++k) {
         const u32 p = w * (32 * SAB_GSORT_ITEMS) + k * 32 + lane;
-        bool big = false;
-        if (p < valid) {
-            const int g = gidx[k];
-            if (g < 0) big = lead_big != 0;
-            else big = ((u32)g + 1 == G && tail_big) || (u32)s_heads[g + 1] - (u32)s_heads[g] > SAB_GSORT_MID;
-        }
+        const bool big = p < valid && gsort_place(s_key, s_val, s_or2, s_oval, s_heads, p, gidx[k], G, tail_big, lead_big);
         bigb[k] = __ballot_sync(SAB_FULL, big);
         mine += (u32)__popc(bigb[k]);
-    }
-    u32 wpre, total;
-    warp_aggregates<u32, CountOp>(mine, CountOp(), 0u, wpre, total);
-    if (w == 0) {
-        const u32 pre = tile_exclusive_prefix_warp<u32, CountOp>(st, tile, total, CountOp(), 0u);
-        if (lane == 0) s_edge[4] = pre;
-    }
-
-    // 4. small groups by the counting rank; records of big groups keep their place (the scatter-back overwrites it)
-#pragma unroll
-    for (int k = 0; k < SAB_GSORT_ITEMS; ++k) {
-        const u32 p = w * (32 * SAB_GSORT_ITEMS) + k * 32 + lane;
-        if (p < valid) gsort_place(s_key, s_val, s_or2, s_oval, s_heads, p, gidx[k], G, tail_big, lead_big);
     }
     // the fetched tail of the last group (a group that is small or of moderate size: never "big")
     if (tid < ext) gsort_place(s_key, s_val, s_or2, s_oval, s_heads, valid + tid, (int)G - 1, G, tail_big, lead_big);
 
-    // 5. groups of moderate size: one warp each, in registers; the warps take them from a shared counter (a tile of
-    // ~256-record groups holds 8 or 9 of them for its 8 warps)
+    // 4. groups of moderate size: one warp each, in registers
     const u32 nmid = s_nmid;
-    for (;;) {
+#if SAB_GSORT_DYNAMIC
+    for (;;) {  // the warps take the groups from a shared counter
         u32 t = 0;
         if (lane == 0) t = atomicAdd(&s_next, 1u);
         t = __shfl_sync(SAB_FULL, t, 0);
         if (t > nmid) break;
+#else
+    for (u32 t = w; t <= nmid; t += SAB_SCAN_WARPS) {
+#endif
         u32 g;
         if (t < nmid) {
             g = s_mid[t];
@@ -339,10 +332,11 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
         else warp_sort_group<16>(s_key + 1 + a, s_val + a, s_or2 + a, s_oval + a, size, lane);
 #endif
     }
-    __syncthreads();
 
-    // 6. records of big groups, compacted in list order
-    const u32 prefix = s_edge[4];
+    // 5. records of big groups, compacted in list order
+    u32 wpre, total;
+    warp_aggregates<u32, CountOp>(mine, CountOp(), 0u, wpre, total);
+    const u32 prefix = tile_exclusive_prefix<u32, CountOp>(st, tile, total, CountOp(), 0u);
     u32 run = prefix + wpre;
 #pragma unroll
     for (int k = 0; k < SAB_GSORT_ITEMS; ++k) {
@@ -358,6 +352,7 @@ group_sort_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64 
         run += (u32)__popc(bigb[k]);
     }
     if (tid == 0 && base + SAB_GSORT_TILE >= m) *d_nbig = prefix + total;  // last tile
+    __syncthreads();
     for (u32 p = skip + tid; p < cnt; p += SAB_GSORT_THREADS) {
         kout[base + p] = (s_key[p + 1] & 0xffffffff00000000ull) | (u64)s_or2[p];  // a slot keeps its first rank
         vout[base + p] = s_oval[p];

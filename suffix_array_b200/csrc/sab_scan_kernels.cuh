@@ -284,13 +284,14 @@ mark_split_groups_kernel(const u64* __restrict__ key64, u64 m, u32* __restrict__
         r1 = (u32)(b >> 32);
         split = (a >> 32) == (b >> 32) && (u32)a != (u32)b;
     }
-    // One atomic per warp and group, and none once the bit is set: in a group of a million records nearly every
-    // neighbouring pair differs, and a million atomics on one word serialise in the L2 (natural-language texts:
-    // this kernel took longer than the sort of the round).
-    const u32 peers = __match_any_sync(SAB_FULL, split ? (u64)r1 : (0x100000000ull | lane_id()));
-    if (split && lane_id() == (u32)(__ffs((int)peers) - 1)) {
+    // At most one atomic per run of neighbouring lanes of a group, and none once the bit is set: in a group of a
+    // million records nearly every neighbouring pair differs, and a million atomics on one word serialise in the L2
+    // (1 GiB mixed text: 86 ms for this kernel, more than the sort of the round).
+    const u32 prev_r1 = __shfl_up_sync(SAB_FULL, r1, 1);
+    const u32 prev_split = __shfl_up_sync(SAB_FULL, (u32)split, 1);
+    if (split && !(lane_id() > 0 && prev_split && prev_r1 == r1)) {
         const u32 bit = 1u << (r1 & 31u);
-        if (!(ld_acquire_u32(&bitmap[r1 >> 5]) & bit)) atomicOr(&bitmap[r1 >> 5], bit);
+        if (!(ld_relaxed_u32(&bitmap[r1 >> 5]) & bit)) atomicOr(&bitmap[r1 >> 5], bit);
     }
 }
 
