@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 20 (1 GPU): final single-GPU state -- A/B (static vs dynamic distribution of the warp sorts),
-# whole GPU suite, smoke, headline bench line, 256 MiB repetitive bench line
+# whole GPU suite, smoke, headline bench line
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -11,5 +11,3 @@ tail -8 gpurun_out/r2_gpu_tests_run20.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke_run20.log 2>&1; tail -2 gpurun_out/r2_smoke_run20.log
 timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_n1_run20.json 2> gpurun_out/r2_bench_n1_run20.err
 tail -c 1200 gpurun_out/r2_bench_n1_run20.json; tail -3 gpurun_out/r2_bench_n1_run20.err
-timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline --no-search > gpurun_out/r2_bench_c3_run20.json 2> gpurun_out/r2_bench_c3_run20.err
-tail -c 600 gpurun_out/r2_bench_c3_run20.json
