@@ -63,6 +63,31 @@ def test_emu_prefix_directory_queries(emu_backend, oracle):
         assert entries == int(sigma.value) ** int(depth.value) and entries >= 2, (entries, sigma.value, depth.value)
 
 
+def test_emu_probe_counter_and_directory_switch(emu_backend, oracle, monkeypatch):
+    """sab200_index_probes counts the suffix comparisons of search_all; with the prefix directory a batch needs
+    fewer of them than with SAB_SEARCH_DIR=0 (bisection of the whole bucket), and both give the oracle's answers."""
+    from suffix_array_b200 import SuffixArray
+    rng = np.random.default_rng(5)
+    s = rng.integers(0, 4, 60000, dtype=np.uint8)
+    pats = pc.random_patterns(rng, s, 300, max_len=40)
+    flat = np.frombuffer(b"".join(pats), dtype=np.uint8)
+    offs = np.zeros(len(pats) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(p) for p in pats])
+    exp_sa = oracle.saca(s)
+    elo, ehi = oracle.search_all_batch(s, exp_sa, None, flat, offs)
+    counts = {}
+    for switch in ("1", "0"):
+        monkeypatch.setenv("SAB_SEARCH_DIR", switch)
+        sa = SuffixArray(s)
+        ix = sa._get_index()
+        assert (emu_backend.sab200_index_directory(ix, None, None) > 0) == (switch == "1")
+        assert emu_backend.sab200_index_probes(ix, 1) == 0
+        lo, hi = sa.search_all_batch(flat, offs)
+        counts[switch] = emu_backend.sab200_index_probes(ix, 0)
+        assert np.array_equal(lo, elo) and np.array_equal(hi, ehi)
+    assert 0 < counts["1"] < counts["0"] / 2, counts
+
+
 def test_emu_fused_buckets(emu_backend, oracle):
     """Bucket table from the sorted keys of the construction: absent bytes, \\0 / \\xff, one symbol per key (falls
     back to the pair counting over the resident text), all 256 byte values, 255 values (radix 2^8: base^k = 2^64)."""
