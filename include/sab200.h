@@ -114,7 +114,9 @@ int32_t sab200_lcp_array(const uint8_t* s, uint64_t n, const uint32_t* sa, uint6
  * sa_len must be n + 1 (NULL is returned otherwise): the safe mirrors can hold a stale array after the
  * reference's set() quirk (src/sa.rs:30-33 keeps the old text), and a short one must not be over-read.
  * Entries of `sa` larger than n (only reachable through unchecked_from_parts) are treated as the empty
- * suffix by the kernels instead of indexing outside the text. */
+ * suffix by the kernels instead of indexing outside the text.
+ * Device memory per replica: n + 4(n + 1) bytes, the bucket table, and the library-private prefix directory of at
+ * most 2^27 + 1 u32 entries (one sweep over the suffix array at creation; see sab200_index_directory below). */
 typedef struct sab200_index sab200_index;
 sab200_index* sab200_index_create(const uint8_t* s, uint64_t n, const uint32_t* sa, uint64_t sa_len,
                                   const uint32_t* bkt_or_null, int32_t ngpus);
