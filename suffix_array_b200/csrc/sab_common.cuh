@@ -90,6 +90,13 @@ __device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
 #endif
 }
 
+// all earlier memory accesses of the thread (loads included) are performed before its later ones, at GPU scope
+__device__ __forceinline__ void fence_acq_rel_gpu() {
+#ifndef SAB_EMU
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ u32 warp_id() { return threadIdx.x >> 5; }
 __device__ __forceinline__ u32 lanemask_lt() { return (1u << (threadIdx.x & 31u)) - 1u; }

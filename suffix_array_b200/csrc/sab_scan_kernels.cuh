@@ -308,9 +308,12 @@ struct FilterScanOp {
     }
 };
 
-// key64 / idx_io are compacted IN PLACE: a tile's output range ends before its own input, every warp
-// of the tile has its input in registers before the barrier, and the range is only written once every
-// predecessor tile has published its aggregate, i.e. has read its input too.
+// key64 / idx_io are compacted IN PLACE: a tile's output range ends before its own input, and the range is only
+// written once every predecessor tile has published its aggregate.  A predecessor must therefore have READ its
+// input by then: the key loads feed the counts it publishes, the index loads feed nothing before the publication,
+// so every thread fences after its loads (a load that is merely issued could still be overtaken by the stores of a
+// later tile; ADVICE r1, and an intermittent wrong suffix array on a 12 MiB repetitive text in round 2 -- once in
+// about ten runs of tests/test_gpu_parity.py::test_filter_and_group_sort_rounds).
 __global__ void __launch_bounds__(SAB_SCAN_THREADS)
 split_filter_kernel(u64* key64, u32* idx_io, u64 m, const u32* __restrict__ bitmap, u32* __restrict__ stay_r1,
                     u32* __restrict__ stay_idx, u32* __restrict__ d_counts, TileState<FilterScan> st) {
@@ -340,6 +343,7 @@ split_filter_kernel(u64* key64, u32* idx_io, u64 m, const u32* __restrict__ bitm
         mine.sort_cnt += (u32)__popc(sb[k]);
         mine.stay_cnt += (u32)__popc(vb[k]);
     }
+    fence_acq_rel_gpu();  // the loads above are performed before anything this block publishes (see the comment above)
     FilterScan ident;
     ident.sort_cnt = 0;
     ident.stay_cnt = 0;
